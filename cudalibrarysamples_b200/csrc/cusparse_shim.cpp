@@ -1,0 +1,490 @@
+// cusparse_shim.cpp -- the drop-in boundary: re-exports the cuSPARSE generic-API symbols that the reference's
+// cuSPARSE/spmv_csr, spmv_coo, spmv_sell, cg and bicgstab samples call, and routes cusparseSpMV /
+// cusparseSpMV_bufferSize / cusparseSpMV_preprocess to the hand-written sm_100a kernels (b200spmv_*).
+//
+// Descriptors stay REAL cuSPARSE descriptors (created by the real library reached through dlopen), so they remain
+// valid for everything the samples hand them to afterwards -- cusparseSpSV_* on matL (cg_example.c:392-402,168-181),
+// cusparseSpMatSetAttribute (cg_example.c:396-402), cusparseDcsric02 ... -- while a side table remembers what our
+// kernels need (pointers, sizes, index base, SELL slice size: CUDA 12.9 has no cusparseSlicedEllGet).
+//
+// Anything we do not implement (transpose, 64-bit indices, mixed precision, complex, CSC/BSR/BlockedELL) is forwarded to
+// the real library, so nothing regresses.  B200SPMV_FORWARD=1 forwards everything (A/B runs with one binary).
+#include <cuda_runtime_api.h>
+#include <cusparse.h>
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/b200spmv.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// the real library
+// ------------------------------------------------------------------------------------------------
+struct Real {
+    void* h = nullptr;
+#define REAL_FN(name) decltype(&::name) name = nullptr;
+    REAL_FN(cusparseCreateCsr)
+    REAL_FN(cusparseCreateConstCsr)
+    REAL_FN(cusparseCreateCoo)
+    REAL_FN(cusparseCreateConstCoo)
+    REAL_FN(cusparseCreateSlicedEll)
+    REAL_FN(cusparseCreateConstSlicedEll)
+    REAL_FN(cusparseDestroySpMat)
+    REAL_FN(cusparseCsrSetPointers)
+    REAL_FN(cusparseCooSetPointers)
+    REAL_FN(cusparseSpMatSetValues)
+    REAL_FN(cusparseCreateDnVec)
+    REAL_FN(cusparseCreateConstDnVec)
+    REAL_FN(cusparseDestroyDnVec)
+    REAL_FN(cusparseDnVecSetValues)
+    REAL_FN(cusparseSpMV_bufferSize)
+    REAL_FN(cusparseSpMV_preprocess)
+    REAL_FN(cusparseSpMV)
+    REAL_FN(cusparseGetStream)
+    REAL_FN(cusparseGetPointerMode)
+    REAL_FN(cusparseSpMatGetFormat)
+    REAL_FN(cusparseConstCsrGet)
+    REAL_FN(cusparseConstCooGet)
+    REAL_FN(cusparseConstDnVecGet)
+#undef REAL_FN
+    bool forward = false, log = false;
+};
+
+Real*          g_real = nullptr;
+std::once_flag g_once;
+
+void init_real() {
+    Real* r = new Real();
+    const char* fwd = getenv("B200SPMV_FORWARD");
+    const char* lg = getenv("B200SPMV_LOG");
+    r->forward = fwd && fwd[0] && fwd[0] != '0';
+    r->log = lg && lg[0] && lg[0] != '0';
+    const char* path = getenv("B200SPMV_CUSPARSE");
+    const char* cands[] = {path, "libcusparse.so.12", "/usr/local/cuda/lib64/libcusparse.so.12", "libcusparse.so"};
+    for (const char* c : cands) {
+        if (!c || !c[0]) continue;
+        r->h = dlopen(c, RTLD_NOW | RTLD_LOCAL);
+        if (r->h) break;
+    }
+    if (!r->h) {
+        fprintf(stderr, "[b200spmv] FATAL: cannot dlopen the real libcusparse.so.12 (%s); set B200SPMV_CUSPARSE\n", dlerror());
+        abort();
+    }
+#define LOAD(name)                                                                                   \
+    r->name = (decltype(r->name))dlsym(r->h, #name);                                                 \
+    if (!r->name) { fprintf(stderr, "[b200spmv] FATAL: real libcusparse lacks %s\n", #name); abort(); }
+    LOAD(cusparseCreateCsr) LOAD(cusparseCreateConstCsr) LOAD(cusparseCreateCoo) LOAD(cusparseCreateConstCoo)
+    LOAD(cusparseCreateSlicedEll) LOAD(cusparseCreateConstSlicedEll) LOAD(cusparseDestroySpMat)
+    LOAD(cusparseCsrSetPointers) LOAD(cusparseCooSetPointers) LOAD(cusparseSpMatSetValues) LOAD(cusparseCreateDnVec)
+    LOAD(cusparseCreateConstDnVec) LOAD(cusparseDestroyDnVec) LOAD(cusparseDnVecSetValues)
+    LOAD(cusparseSpMV_bufferSize) LOAD(cusparseSpMV_preprocess) LOAD(cusparseSpMV) LOAD(cusparseGetStream)
+    LOAD(cusparseGetPointerMode) LOAD(cusparseSpMatGetFormat) LOAD(cusparseConstCsrGet) LOAD(cusparseConstCooGet)
+    LOAD(cusparseConstDnVecGet)
+#undef LOAD
+    g_real = r;
+}
+
+inline Real& real() {
+    std::call_once(g_once, init_real);
+    return *g_real;
+}
+
+// ------------------------------------------------------------------------------------------------
+// side tables
+// ------------------------------------------------------------------------------------------------
+struct MatInfo {
+    uint64_t             uid = 0;
+    cusparseFormat_t     format = CUSPARSE_FORMAT_CSR;
+    int64_t              rows = 0, cols = 0, nnz = 0;
+    const void *         offsets = nullptr, *row_ind = nullptr, *col_ind = nullptr, *values = nullptr;
+    cusparseIndexType_t  off_type = CUSPARSE_INDEX_32I, col_type = CUSPARSE_INDEX_32I;
+    cusparseIndexBase_t  base = CUSPARSE_INDEX_BASE_ZERO;
+    cudaDataType         vtype = CUDA_R_32F;
+    int64_t              sell_values_size = 0, slice_size = 0;
+    void*                plan_buffer = nullptr;  // externalBuffer currently holding this matrix' CSR plan
+};
+struct VecInfo {
+    int64_t      size = 0;
+    const void*  values = nullptr;
+    cudaDataType vtype = CUDA_R_32F;
+};
+
+std::mutex                                  g_mu;
+std::unordered_map<const void*, MatInfo>    g_mats;
+std::unordered_map<const void*, VecInfo>    g_vecs;
+std::unordered_map<const void*, uint64_t>   g_plan_owner;  // externalBuffer -> uid of the matrix whose plan it holds
+std::atomic<uint64_t>                       g_uid{1};
+
+bool find_mat(cusparseConstSpMatDescr_t d, MatInfo* out) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_mats.find((const void*)d);
+        if (it != g_mats.end()) { *out = it->second; return true; }
+    }
+    // Descriptor created behind our back (e.g. by a library that bound the real symbol directly): ask the real getters.
+    Real& R = real();
+    cusparseFormat_t f;
+    if (R.cusparseSpMatGetFormat(d, &f) != CUSPARSE_STATUS_SUCCESS) return false;
+    MatInfo m;
+    m.format = f;
+    if (f == CUSPARSE_FORMAT_CSR) {
+        if (R.cusparseConstCsrGet(d, &m.rows, &m.cols, &m.nnz, &m.offsets, &m.col_ind, &m.values, &m.off_type, &m.col_type,
+                                  &m.base, &m.vtype) != CUSPARSE_STATUS_SUCCESS)
+            return false;
+    } else if (f == CUSPARSE_FORMAT_COO) {
+        if (R.cusparseConstCooGet(d, &m.rows, &m.cols, &m.nnz, &m.row_ind, &m.col_ind, &m.values, &m.col_type, &m.base,
+                                  &m.vtype) != CUSPARSE_STATUS_SUCCESS)
+            return false;
+        m.off_type = m.col_type;
+    } else {
+        return false;
+    }
+    m.uid = g_uid++;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_mats[(const void*)d] = m;
+    *out = m;
+    return true;
+}
+
+bool find_vec(cusparseConstDnVecDescr_t d, VecInfo* out) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_vecs.find((const void*)d);
+        if (it != g_vecs.end()) { *out = it->second; return true; }
+    }
+    VecInfo v;
+    if (real().cusparseConstDnVecGet(d, &v.size, &v.values, &v.vtype) != CUSPARSE_STATUS_SUCCESS) return false;
+    *out = v;
+    return true;
+}
+
+void record_mat(const void* d, const MatInfo& m) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    MatInfo mm = m;
+    mm.uid = g_uid++;
+    g_mats[d] = mm;
+}
+
+inline int dtype_of(cudaDataType t) { return t == CUDA_R_32F ? 0 : (t == CUDA_R_64F ? 1 : -1); }
+
+// Can our kernels take this call?  (Everything else is forwarded to the real library.)
+bool supported(cusparseOperation_t op, const MatInfo& m, const VecInfo& x, const VecInfo& y, cudaDataType compute) {
+    if (op != CUSPARSE_OPERATION_NON_TRANSPOSE) return false;
+    if (dtype_of(m.vtype) < 0 || x.vtype != m.vtype || y.vtype != m.vtype || compute != m.vtype) return false;
+    if (m.off_type != CUSPARSE_INDEX_32I || m.col_type != CUSPARSE_INDEX_32I) return false;
+    if (m.format != CUSPARSE_FORMAT_CSR && m.format != CUSPARSE_FORMAT_COO && m.format != CUSPARSE_FORMAT_SLICED_ELLPACK) return false;
+    if (m.rows >= INT32_MAX || m.cols >= INT32_MAX || m.nnz >= INT32_MAX - 8) return false;
+    return true;
+}
+
+cusparseStatus_t to_status(int rc) {
+    if (rc == 0) return CUSPARSE_STATUS_SUCCESS;
+    if (rc == -1) return CUSPARSE_STATUS_INVALID_VALUE;
+    return CUSPARSE_STATUS_EXECUTION_FAILED;
+}
+
+void logf(const char* what, const MatInfo& m) {
+    if (real().log)
+        fprintf(stderr, "[b200spmv] %s fmt=%d rows=%lld cols=%lld nnz=%lld vtype=%d base=%d\n", what, (int)m.format,
+                (long long)m.rows, (long long)m.cols, (long long)m.nnz, (int)m.vtype, (int)m.base);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200spmv_version(void) { return "b200spmv 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------- sparse-matrix descriptors --------------------------
+cusparseStatus_t cusparseCreateCsr(cusparseSpMatDescr_t* d, int64_t rows, int64_t cols, int64_t nnz, void* off, void* col,
+                                   void* val, cusparseIndexType_t offT, cusparseIndexType_t colT, cusparseIndexBase_t base,
+                                   cudaDataType vT) {
+    cusparseStatus_t st = real().cusparseCreateCsr(d, rows, cols, nnz, off, col, val, offT, colT, base, vT);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        MatInfo m;
+        m.format = CUSPARSE_FORMAT_CSR; m.rows = rows; m.cols = cols; m.nnz = nnz; m.offsets = off; m.col_ind = col;
+        m.values = val; m.off_type = offT; m.col_type = colT; m.base = base; m.vtype = vT;
+        record_mat((const void*)*d, m);
+    }
+    return st;
+}
+
+cusparseStatus_t cusparseCreateConstCsr(cusparseConstSpMatDescr_t* d, int64_t rows, int64_t cols, int64_t nnz,
+                                        const void* off, const void* col, const void* val, cusparseIndexType_t offT,
+                                        cusparseIndexType_t colT, cusparseIndexBase_t base, cudaDataType vT) {
+    cusparseStatus_t st = real().cusparseCreateConstCsr(d, rows, cols, nnz, off, col, val, offT, colT, base, vT);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        MatInfo m;
+        m.format = CUSPARSE_FORMAT_CSR; m.rows = rows; m.cols = cols; m.nnz = nnz; m.offsets = off; m.col_ind = col;
+        m.values = val; m.off_type = offT; m.col_type = colT; m.base = base; m.vtype = vT;
+        record_mat((const void*)*d, m);
+    }
+    return st;
+}
+
+cusparseStatus_t cusparseCreateCoo(cusparseSpMatDescr_t* d, int64_t rows, int64_t cols, int64_t nnz, void* row, void* col,
+                                   void* val, cusparseIndexType_t idxT, cusparseIndexBase_t base, cudaDataType vT) {
+    cusparseStatus_t st = real().cusparseCreateCoo(d, rows, cols, nnz, row, col, val, idxT, base, vT);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        MatInfo m;
+        m.format = CUSPARSE_FORMAT_COO; m.rows = rows; m.cols = cols; m.nnz = nnz; m.row_ind = row; m.col_ind = col;
+        m.values = val; m.off_type = idxT; m.col_type = idxT; m.base = base; m.vtype = vT;
+        record_mat((const void*)*d, m);
+    }
+    return st;
+}
+
+cusparseStatus_t cusparseCreateConstCoo(cusparseConstSpMatDescr_t* d, int64_t rows, int64_t cols, int64_t nnz,
+                                        const void* row, const void* col, const void* val, cusparseIndexType_t idxT,
+                                        cusparseIndexBase_t base, cudaDataType vT) {
+    cusparseStatus_t st = real().cusparseCreateConstCoo(d, rows, cols, nnz, row, col, val, idxT, base, vT);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        MatInfo m;
+        m.format = CUSPARSE_FORMAT_COO; m.rows = rows; m.cols = cols; m.nnz = nnz; m.row_ind = row; m.col_ind = col;
+        m.values = val; m.off_type = idxT; m.col_type = idxT; m.base = base; m.vtype = vT;
+        record_mat((const void*)*d, m);
+    }
+    return st;
+}
+
+cusparseStatus_t cusparseCreateSlicedEll(cusparseSpMatDescr_t* d, int64_t rows, int64_t cols, int64_t nnz,
+                                         int64_t valuesSize, int64_t sliceSize, void* sliceOff, void* col, void* val,
+                                         cusparseIndexType_t offT, cusparseIndexType_t colT, cusparseIndexBase_t base,
+                                         cudaDataType vT) {
+    cusparseStatus_t st =
+        real().cusparseCreateSlicedEll(d, rows, cols, nnz, valuesSize, sliceSize, sliceOff, col, val, offT, colT, base, vT);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        MatInfo m;
+        m.format = CUSPARSE_FORMAT_SLICED_ELLPACK; m.rows = rows; m.cols = cols; m.nnz = nnz; m.offsets = sliceOff;
+        m.col_ind = col; m.values = val; m.off_type = offT; m.col_type = colT; m.base = base; m.vtype = vT;
+        m.sell_values_size = valuesSize; m.slice_size = sliceSize;
+        record_mat((const void*)*d, m);
+    }
+    return st;
+}
+
+cusparseStatus_t cusparseCreateConstSlicedEll(cusparseConstSpMatDescr_t* d, int64_t rows, int64_t cols, int64_t nnz,
+                                              int64_t valuesSize, int64_t sliceSize, const void* sliceOff, const void* col,
+                                              const void* val, cusparseIndexType_t offT, cusparseIndexType_t colT,
+                                              cusparseIndexBase_t base, cudaDataType vT) {
+    cusparseStatus_t st = real().cusparseCreateConstSlicedEll(d, rows, cols, nnz, valuesSize, sliceSize, sliceOff, col, val,
+                                                              offT, colT, base, vT);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        MatInfo m;
+        m.format = CUSPARSE_FORMAT_SLICED_ELLPACK; m.rows = rows; m.cols = cols; m.nnz = nnz; m.offsets = sliceOff;
+        m.col_ind = col; m.values = val; m.off_type = offT; m.col_type = colT; m.base = base; m.vtype = vT;
+        m.sell_values_size = valuesSize; m.slice_size = sliceSize;
+        record_mat((const void*)*d, m);
+    }
+    return st;
+}
+
+cusparseStatus_t cusparseDestroySpMat(cusparseConstSpMatDescr_t d) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_mats.find((const void*)d);
+        if (it != g_mats.end()) {
+            if (it->second.plan_buffer) {
+                auto ow = g_plan_owner.find(it->second.plan_buffer);
+                if (ow != g_plan_owner.end() && ow->second == it->second.uid) g_plan_owner.erase(ow);
+            }
+            g_mats.erase(it);
+        }
+    }
+    return real().cusparseDestroySpMat(d);
+}
+
+cusparseStatus_t cusparseCsrSetPointers(cusparseSpMatDescr_t d, void* off, void* col, void* val) {
+    cusparseStatus_t st = real().cusparseCsrSetPointers(d, off, col, val);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_mats.find((const void*)d);
+        if (it != g_mats.end()) {
+            it->second.offsets = off; it->second.col_ind = col; it->second.values = val;
+            it->second.plan_buffer = nullptr;  // structure may have changed: re-analyse on the next SpMV
+        }
+    }
+    return st;
+}
+
+cusparseStatus_t cusparseCooSetPointers(cusparseSpMatDescr_t d, void* row, void* col, void* val) {
+    cusparseStatus_t st = real().cusparseCooSetPointers(d, row, col, val);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_mats.find((const void*)d);
+        if (it != g_mats.end()) { it->second.row_ind = row; it->second.col_ind = col; it->second.values = val; }
+    }
+    return st;
+}
+
+cusparseStatus_t cusparseSpMatSetValues(cusparseSpMatDescr_t d, void* val) {
+    cusparseStatus_t st = real().cusparseSpMatSetValues(d, val);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_mats.find((const void*)d);
+        if (it != g_mats.end()) it->second.values = val;  // the plan is structure-only: still valid
+    }
+    return st;
+}
+
+// ---------------------------------------------------------------- dense-vector descriptors ---------------------------
+cusparseStatus_t cusparseCreateDnVec(cusparseDnVecDescr_t* d, int64_t size, void* values, cudaDataType vT) {
+    cusparseStatus_t st = real().cusparseCreateDnVec(d, size, values, vT);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        VecInfo v; v.size = size; v.values = values; v.vtype = vT;
+        g_vecs[(const void*)*d] = v;
+    }
+    return st;
+}
+
+cusparseStatus_t cusparseCreateConstDnVec(cusparseConstDnVecDescr_t* d, int64_t size, const void* values, cudaDataType vT) {
+    cusparseStatus_t st = real().cusparseCreateConstDnVec(d, size, values, vT);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        VecInfo v; v.size = size; v.values = values; v.vtype = vT;
+        g_vecs[(const void*)*d] = v;
+    }
+    return st;
+}
+
+cusparseStatus_t cusparseDestroyDnVec(cusparseConstDnVecDescr_t d) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_vecs.erase((const void*)d);
+    }
+    return real().cusparseDestroyDnVec(d);
+}
+
+cusparseStatus_t cusparseDnVecSetValues(cusparseDnVecDescr_t d, void* values) {
+    cusparseStatus_t st = real().cusparseDnVecSetValues(d, values);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_vecs.find((const void*)d);
+        if (it != g_vecs.end()) it->second.values = values;
+    }
+    return st;
+}
+
+// ---------------------------------------------------------------- SpMV -----------------------------------------------
+cusparseStatus_t cusparseSpMV_bufferSize(cusparseHandle_t handle, cusparseOperation_t opA, const void* alpha,
+                                         cusparseConstSpMatDescr_t matA, cusparseConstDnVecDescr_t vecX, const void* beta,
+                                         cusparseDnVecDescr_t vecY, cudaDataType computeType, cusparseSpMVAlg_t alg,
+                                         size_t* bufferSize) {
+    Real& R = real();
+    if (R.forward) return R.cusparseSpMV_bufferSize(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, bufferSize);
+    if (!handle || !matA || !vecX || !vecY || !bufferSize) return CUSPARSE_STATUS_INVALID_VALUE;
+    // Always ask the real library too: if a later call has to be forwarded, the caller's buffer must be big enough.
+    size_t real_size = 0;
+    cusparseStatus_t st = R.cusparseSpMV_bufferSize(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, &real_size);
+    MatInfo m; VecInfo x, y;
+    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType)) {
+        *bufferSize = real_size;
+        return st;
+    }
+    if (st != CUSPARSE_STATUS_SUCCESS) return st;  // the real library rejected the arguments: keep its verdict
+    size_t ours = 0;
+    if (m.format == CUSPARSE_FORMAT_CSR) ours = b200spmv_csr_workspace_bytes(m.rows, m.nnz);
+    else if (m.format == CUSPARSE_FORMAT_COO) ours = b200spmv_coo_workspace_bytes(m.rows, m.nnz);
+    else ours = b200spmv_sell_workspace_bytes(m.rows, m.sell_values_size, m.slice_size);
+    *bufferSize = ours > real_size ? ours : real_size;
+    {
+        // A fresh bufferSize query usually precedes a fresh cudaMalloc: never trust an older plan after it.
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_mats.find((const void*)matA);
+        if (it != g_mats.end()) it->second.plan_buffer = nullptr;
+    }
+    return CUSPARSE_STATUS_SUCCESS;
+}
+
+static cusparseStatus_t ensure_csr_plan(cudaStream_t stream, cusparseConstSpMatDescr_t matA, const MatInfo& m, void* buffer,
+                                        bool force) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!force && m.plan_buffer == buffer) {
+            auto ow = g_plan_owner.find(buffer);
+            if (ow != g_plan_owner.end() && ow->second == m.uid) return CUSPARSE_STATUS_SUCCESS;
+        }
+    }
+    int rc = b200spmv_csr_analyze((void*)stream, m.rows, m.nnz, m.offsets, (int32_t)m.base, buffer);
+    if (rc != 0) return to_status(rc);
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_mats.find((const void*)matA);
+    if (it != g_mats.end()) it->second.plan_buffer = buffer;
+    g_plan_owner[buffer] = m.uid;
+    return CUSPARSE_STATUS_SUCCESS;
+}
+
+cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t handle, cusparseOperation_t opA, const void* alpha,
+                                         cusparseConstSpMatDescr_t matA, cusparseConstDnVecDescr_t vecX, const void* beta,
+                                         cusparseDnVecDescr_t vecY, cudaDataType computeType, cusparseSpMVAlg_t alg,
+                                         void* externalBuffer) {
+    Real& R = real();
+    if (R.forward) return R.cusparseSpMV_preprocess(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
+    if (!handle || !matA || !vecX || !vecY) return CUSPARSE_STATUS_INVALID_VALUE;
+    MatInfo m; VecInfo x, y;
+    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType))
+        return R.cusparseSpMV_preprocess(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
+    if (x.size != m.cols || y.size != m.rows) return CUSPARSE_STATUS_INVALID_VALUE;
+    if (m.format != CUSPARSE_FORMAT_CSR) return CUSPARSE_STATUS_SUCCESS;  // COO / SELL need no analysis
+    if (!externalBuffer || ((uintptr_t)externalBuffer & 15)) return CUSPARSE_STATUS_INVALID_VALUE;
+    cudaStream_t stream = nullptr;
+    cusparseStatus_t st = R.cusparseGetStream(handle, &stream);
+    if (st != CUSPARSE_STATUS_SUCCESS) return st;
+    logf("preprocess(csr plan)", m);
+    return ensure_csr_plan(stream, matA, m, externalBuffer, /*force=*/true);
+}
+
+cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, const void* alpha,
+                              cusparseConstSpMatDescr_t matA, cusparseConstDnVecDescr_t vecX, const void* beta,
+                              cusparseDnVecDescr_t vecY, cudaDataType computeType, cusparseSpMVAlg_t alg,
+                              void* externalBuffer) {
+    Real& R = real();
+    if (R.forward) return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
+    if (!handle || !matA || !vecX || !vecY || !alpha || !beta) return CUSPARSE_STATUS_INVALID_VALUE;
+    MatInfo m; VecInfo x, y;
+    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType)) {
+        if (R.log) fprintf(stderr, "[b200spmv] SpMV forwarded to libcusparse (unsupported combination)\n");
+        return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
+    }
+    if (x.size != m.cols || y.size != m.rows) return CUSPARSE_STATUS_INVALID_VALUE;
+    cudaStream_t stream = nullptr;
+    cusparseStatus_t st = R.cusparseGetStream(handle, &stream);
+    if (st != CUSPARSE_STATUS_SUCCESS) return st;
+    cusparsePointerMode_t pm = CUSPARSE_POINTER_MODE_HOST;
+    st = R.cusparseGetPointerMode(handle, &pm);
+    if (st != CUSPARSE_STATUS_SUCCESS) return st;
+    const int on_dev = pm == CUSPARSE_POINTER_MODE_DEVICE;
+    const int dt = dtype_of(m.vtype);
+    int rc;
+    if (m.format == CUSPARSE_FORMAT_CSR) {
+        if (m.rows == 0) return CUSPARSE_STATUS_SUCCESS;
+        if (!externalBuffer || ((uintptr_t)externalBuffer & 15)) {
+            // No room for a plan (caller ignored bufferSize): let the real library handle it.
+            return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
+        }
+        st = ensure_csr_plan(stream, matA, m, externalBuffer, /*force=*/false);
+        if (st != CUSPARSE_STATUS_SUCCESS) return st;
+        logf("SpMV csr_tile_kernel", m);
+        rc = b200spmv_csr_mv((void*)stream, dt, m.rows, m.cols, m.nnz, m.offsets, m.col_ind, m.values, (int32_t)m.base, alpha,
+                             beta, on_dev, x.values, (void*)y.values, externalBuffer);
+    } else if (m.format == CUSPARSE_FORMAT_COO) {
+        logf("SpMV coo_tile_kernel", m);
+        rc = b200spmv_coo_mv((void*)stream, dt, m.rows, m.cols, m.nnz, m.row_ind, m.col_ind, m.values, (int32_t)m.base, alpha,
+                             beta, on_dev, x.values, (void*)y.values, externalBuffer);
+    } else {
+        logf("SpMV sell_row_kernel", m);
+        rc = b200spmv_sell_mv((void*)stream, dt, m.rows, m.cols, m.slice_size, m.offsets, m.col_ind, m.values,
+                              (int32_t)m.base, alpha, beta, on_dev, x.values, (void*)y.values, externalBuffer);
+    }
+    return to_status(rc);
+}
+
+}  // extern "C"

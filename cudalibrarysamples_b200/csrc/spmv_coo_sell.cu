@@ -1,0 +1,246 @@
+// spmv_coo_sell.cu -- COO and Sliced-ELL  y = alpha*A*x + beta*y  for B200 (sm_100a), fp32 / fp64, int32 indices.
+//
+// COO replaces cusparse::coomv_kernel behind cusparseSpMV for cusparseCreateCoo descriptors
+//   (cuSPARSE/spmv_coo/spmv_coo_example.c:86-104): SoA row/col/val arrays, usually row-sorted
+//   (spmv_coo_example.c:48-49) but any order is accepted.
+// SELL replaces cusparse::sellmv_v1_kernel behind cusparseSpMV for cusparseCreateSlicedEll descriptors
+//   (cuSPARSE/spmv_sell/spmv_sell_example.c:103-122): column-major inside each slice, padding col = -1.
+#include "spmv_common.cuh"
+#include "../../include/b200spmv.h"
+
+namespace b200 {
+
+// ================================================================================================
+// COO
+//   pass 1: y = beta*y (or 0)                       -- rows without entries must still be scaled
+//   pass 2: tiles of COO_TILE non-zeros; each thread owns COO_PER_THREAD consecutive entries (from
+//           shared memory, after a coalesced 128-bit streaming load), folds runs of equal row index
+//           and issues one fp atomic per run (RED.ADD at L2).  Runs that continue in the neighbouring
+//           thread / tile simply produce one more atomic, so unsorted input stays correct.
+// ================================================================================================
+constexpr int COO_BLOCK = 256;
+constexpr int COO_PER_THREAD = 8;
+constexpr int COO_TILE = COO_BLOCK * COO_PER_THREAD;  // 2048, multiple of 4 -> tile starts stay 16B aligned
+
+template <typename T>
+__global__ void scale_y_kernel(T* __restrict__ y, int64_t rows, Scalars<T> s) {
+    const T beta = s.b();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = beta == T(0) ? T(0) : beta * y[i];
+}
+
+template <typename T>
+struct CooArgs {
+    const int* row;
+    const int* col;
+    const T*   val;
+    const T*   x;
+    T*         y;
+    int        base;
+    int        nnz;
+    int        vec_ok;
+    Scalars<T> s;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(COO_BLOCK) coo_tile_kernel(const CooArgs<T> a) {
+    __shared__ T   sP[COO_TILE + COO_BLOCK / 4];  // padded: index i lives at i + i/32 -> conflict-free strided walk
+    __shared__ int sR[COO_TILE + COO_BLOCK / 4];
+    const int n0 = blockIdx.x * COO_TILE;
+    const int n1 = min(n0 + COO_TILE, a.nnz);
+    const T   alpha = a.s.a();
+    constexpr int ITERS = COO_TILE / (COO_BLOCK * 4);
+    const int nnz_vec_end = a.vec_ok ? (a.nnz & ~3) : 0;
+
+    int r[ITERS][4], c[ITERS][4];
+    T   v[ITERS][4];
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+        const int i0 = n0 + (it * COO_BLOCK + (int)threadIdx.x) * 4;
+        if (i0 < n1) {
+            if (i0 + 4 <= nnz_vec_end) {
+                const int4 rr = ldg_stream_int4(a.row + i0), cc = ldg_stream_int4(a.col + i0);
+                r[it][0] = rr.x; r[it][1] = rr.y; r[it][2] = rr.z; r[it][3] = rr.w;
+                c[it][0] = cc.x; c[it][1] = cc.y; c[it][2] = cc.z; c[it][3] = cc.w;
+                load4_stream(a.val + i0, v[it]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool ok = i0 + j < n1;
+                    r[it][j] = ok ? ldg_stream(a.row + i0 + j) : a.base;
+                    c[it][j] = ok ? ldg_stream(a.col + i0 + j) : a.base;
+                    v[it][j] = ok ? ldg_stream(a.val + i0 + j) : T(0);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+        const int i0 = n0 + (it * COO_BLOCK + (int)threadIdx.x) * 4;
+        if (i0 < n1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = i0 + j - n0;
+                if (i0 + j < n1) {
+                    const T xv = __ldg(a.x + (c[it][j] - a.base));
+                    sP[i + (i >> 5)] = v[it][j] * xv;
+                    sR[i + (i >> 5)] = r[it][j] - a.base;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int cnt = n1 - n0;
+    const int k0 = (int)threadIdx.x * COO_PER_THREAD;
+    if (k0 < cnt) {
+        const int k1 = min(k0 + COO_PER_THREAD, cnt);
+        int cur = sR[k0 + (k0 >> 5)];
+        T   sum = sP[k0 + (k0 >> 5)];
+        for (int k = k0 + 1; k < k1; k++) {
+            const int rr = sR[k + (k >> 5)];
+            const T   p  = sP[k + (k >> 5)];
+            if (rr != cur) {
+                atomicAdd(a.y + cur, alpha * sum);
+                cur = rr; sum = p;
+            } else {
+                sum += p;
+            }
+        }
+        atomicAdd(a.y + cur, alpha * sum);
+    }
+}
+
+template <typename T>
+static int launch_coo(cudaStream_t stream, int64_t rows, int64_t nnz, const void* row, const void* col, const void* val,
+                      int base, const void* alpha, const void* beta, int on_device, const void* x, void* y) {
+    Scalars<T> s;
+    if (on_device) { s.alpha = T(0); s.beta = T(0); s.alpha_dev = (const T*)alpha; s.beta_dev = (const T*)beta; }
+    else { s.alpha = *(const T*)alpha; s.beta = *(const T*)beta; s.alpha_dev = nullptr; s.beta_dev = nullptr; }
+    {
+        const int threads = 256;
+        int64_t blocks = (rows + threads - 1) / threads;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        scale_y_kernel<T><<<(unsigned)blocks, threads, 0, stream>>>((T*)y, rows, s);
+    }
+    if (nnz > 0) {
+        CooArgs<T> a;
+        a.row = (const int*)row; a.col = (const int*)col; a.val = (const T*)val; a.x = (const T*)x; a.y = (T*)y;
+        a.base = base; a.nnz = (int)nnz; a.s = s;
+        a.vec_ok = (((uintptr_t)row | (uintptr_t)col | (uintptr_t)val) & 15) == 0;
+        const unsigned blocks = (unsigned)((nnz + COO_TILE - 1) / COO_TILE);
+        coo_tile_kernel<T><<<blocks, COO_BLOCK, 0, stream>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
+// ================================================================================================
+// Sliced-ELL: one thread per row, slice-column-major storage makes the 32 lanes of a warp read 32
+// consecutive values / column indices for every k (fully coalesced when sliceSize is a multiple of
+// 32); the k loop is unrolled SELL_UNROLL deep so that many independent val/col/x loads are in flight.
+// ================================================================================================
+constexpr int SELL_BLOCK = 256;
+constexpr int SELL_UNROLL = 8;
+
+template <typename T>
+struct SellArgs {
+    const int* slice_off;
+    const int* col;
+    const T*   val;
+    const T*   x;
+    T*         y;
+    int        base;
+    int        rows;
+    int        slice_size;
+    Scalars<T> s;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(SELL_BLOCK) sell_row_kernel(const SellArgs<T> a) {
+    const int row = blockIdx.x * SELL_BLOCK + (int)threadIdx.x;
+    if (row >= a.rows) return;
+    const int C = a.slice_size;
+    const int s = row / C, lane = row - s * C;
+    const int beg = __ldg(a.slice_off + s) - a.base, end = __ldg(a.slice_off + s + 1) - a.base;
+    const int width = (end - beg) / C;
+    const int* cp = a.col + beg + lane;
+    const T*   vp = a.val + beg + lane;
+    T sum = T(0);
+    int k = 0;
+    for (; k + SELL_UNROLL <= width; k += SELL_UNROLL) {
+        int cc[SELL_UNROLL];
+        T   vv[SELL_UNROLL], xx[SELL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SELL_UNROLL; u++) {
+            cc[u] = ldg_stream(cp + (size_t)(k + u) * C) - a.base;
+            vv[u] = ldg_stream(vp + (size_t)(k + u) * C);
+        }
+#pragma unroll
+        for (int u = 0; u < SELL_UNROLL; u++) xx[u] = cc[u] >= 0 ? __ldg(a.x + cc[u]) : T(0);
+#pragma unroll
+        for (int u = 0; u < SELL_UNROLL; u++) sum += vv[u] * xx[u];
+    }
+    for (; k < width; k++) {
+        const int cc = ldg_stream(cp + (size_t)k * C) - a.base;
+        const T   vv = ldg_stream(vp + (size_t)k * C);
+        if (cc >= 0) sum += vv * __ldg(a.x + cc);
+    }
+    T* yp = a.y + row;
+    *yp = axpby(a.s.a(), sum, a.s.b(), yp);
+}
+
+template <typename T>
+static int launch_sell(cudaStream_t stream, int64_t rows, int64_t slice_size, const void* slice_off, const void* col,
+                       const void* val, int base, const void* alpha, const void* beta, int on_device, const void* x,
+                       void* y) {
+    SellArgs<T> a;
+    a.slice_off = (const int*)slice_off; a.col = (const int*)col; a.val = (const T*)val; a.x = (const T*)x; a.y = (T*)y;
+    a.base = base; a.rows = (int)rows; a.slice_size = (int)slice_size;
+    if (on_device) { a.s.alpha = T(0); a.s.beta = T(0); a.s.alpha_dev = (const T*)alpha; a.s.beta_dev = (const T*)beta; }
+    else { a.s.alpha = *(const T*)alpha; a.s.beta = *(const T*)beta; a.s.alpha_dev = nullptr; a.s.beta_dev = nullptr; }
+    const unsigned blocks = (unsigned)((rows + SELL_BLOCK - 1) / SELL_BLOCK);
+    sell_row_kernel<T><<<blocks, SELL_BLOCK, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+size_t b200spmv_coo_workspace_bytes(int64_t, int64_t) { return 0; }
+
+int b200spmv_coo_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz, const void* row_ind,
+                    const void* col_ind, const void* values, int32_t base, const void* alpha, const void* beta,
+                    int scalars_on_device, const void* x, void* y, void* /*workspace*/) {
+    if (rows < 0 || cols < 0 || nnz < 0 || nnz > INT32_MAX - 4 || rows > INT32_MAX - 1 || !alpha || !beta) return -1;
+    if (rows == 0) return 0;
+    if (!y || (nnz > 0 && (!row_ind || !col_ind || !values || !x))) return -1;
+    if (dtype == 0)
+        return launch_coo<float>((cudaStream_t)stream, rows, nnz, row_ind, col_ind, values, base, alpha, beta,
+                                 scalars_on_device, x, y);
+    if (dtype == 1)
+        return launch_coo<double>((cudaStream_t)stream, rows, nnz, row_ind, col_ind, values, base, alpha, beta,
+                                  scalars_on_device, x, y);
+    return -1;
+}
+
+size_t b200spmv_sell_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
+
+int b200spmv_sell_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t slice_size, const void* slice_offsets,
+                     const void* col_ind, const void* values, int32_t base, const void* alpha, const void* beta,
+                     int scalars_on_device, const void* x, void* y, void* /*workspace*/) {
+    if (rows < 0 || cols < 0 || slice_size <= 0 || rows > INT32_MAX - 1 || !alpha || !beta) return -1;
+    if (rows == 0) return 0;
+    if (!y || !slice_offsets) return -1;
+    if (dtype == 0)
+        return launch_sell<float>((cudaStream_t)stream, rows, slice_size, slice_offsets, col_ind, values, base, alpha,
+                                  beta, scalars_on_device, x, y);
+    if (dtype == 1)
+        return launch_sell<double>((cudaStream_t)stream, rows, slice_size, slice_offsets, col_ind, values, base, alpha,
+                                   beta, scalars_on_device, x, y);
+    return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,336 @@
+// spmv_csr.cu -- CSR  y = alpha*A*x + beta*y  for B200 (sm_100a), fp32 / fp64, int32 indices.
+//
+// Replaces the closed cusparse::partition_kernel / csrmv_v3_kernel / spmv_fixup_kernel trio behind
+// cusparseSpMV_preprocess / cusparseSpMV (reference call sites: cuSPARSE/spmv_csr/spmv_csr_example.c:104-112,
+// cuSPARSE/cg/cg_example.c:156,220,294,415, cuSPARSE/bicgstab/bicgstab_example.c:190,262,315,358,504).
+//
+// Design (see DESIGN.md "CSR kernel"):
+//   * analyze: merge-path style partition of the (rows + nnz) item list into tiles of TILE_ITEMS items.
+//     A tile boundary that falls inside a row shorter than LONG_ROW is rounded down to that row's start,
+//     so ordinary rows never straddle tiles and need no carry/fix-up; only rows >= LONG_ROW are cut, and
+//     their per-tile partial sums are combined by the last-arriving tile (arrival counter, fixed
+//     summation order -> bit-reproducible, single launch, no spin-waits).
+//   * mv: one CTA per tile.  Phase 1 streams val[]/col_ind[] with 128-bit L1-bypassing loads
+//     (coalesced, all loads of the tile in flight before the first use), gathers x through L1/L2 and
+//     parks the products in shared memory.  Phase 2 reduces each row from shared memory with a group of
+//     g = 1..32 lanes (g picked per tile from its mean row length) and a warp-shuffle tree, and writes y
+//     once.  No tensor cores: 0.125-0.17 flop/B, HBM-bound.
+#include "spmv_common.cuh"
+#include "../../include/b200spmv.h"
+
+namespace b200 {
+
+constexpr int CSR_TILE_ITEMS = 2048;  // merge items (row ends + non-zeros) per tile
+constexpr int CSR_LONG_ROW   = 512;   // rows at least this long may be split between tiles
+constexpr int CSR_BLOCK      = 256;   // threads per CTA
+constexpr int CSR_SMEM_ELEMS = CSR_TILE_ITEMS + CSR_LONG_ROW;  // max non-zeros a tile can hold
+constexpr int CSR_VEC        = 4;     // non-zeros per thread per load step (128-bit col load)
+constexpr int CSR_ITERS      = (CSR_SMEM_ELEMS + CSR_VEC - 1 + CSR_BLOCK * CSR_VEC - 1) / (CSR_BLOCK * CSR_VEC);
+
+constexpr size_t PLAN_HEADER_BYTES = 256;
+
+struct PlanView {
+    int2*   tiles;      // [num_tiles+1] (row, nnz) start coordinate of each tile
+    int*    counters;   // [num_tiles+1] arrival counters of split rows, indexed by the row's first tile
+    double* head_part;  // [num_tiles+1] partial sum of the split row a tile starts in
+    double* tail_part;  // [num_tiles+1] partial sum of the split row a tile ends in
+};
+
+static inline int64_t csr_num_tiles(int64_t rows, int64_t nnz) {
+    return (rows + nnz + CSR_TILE_ITEMS - 1) / CSR_TILE_ITEMS;
+}
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static inline size_t plan_layout(int64_t num_tiles, void* ws, PlanView* v) {
+    size_t n = (size_t)num_tiles + 1;
+    size_t o_tiles = PLAN_HEADER_BYTES;
+    size_t o_cnt   = align_up(o_tiles + n * sizeof(int2), 256);
+    size_t o_head  = align_up(o_cnt + n * sizeof(int), 256);
+    size_t o_tail  = align_up(o_head + n * sizeof(double), 256);
+    size_t total   = align_up(o_tail + n * sizeof(double), 256);
+    if (v) {
+        char* b = (char*)ws;
+        v->tiles = (int2*)(b + o_tiles);
+        v->counters = (int*)(b + o_cnt);
+        v->head_part = (double*)(b + o_head);
+        v->tail_part = (double*)(b + o_tail);
+    }
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// analyze: one thread per tile boundary.
+//   boundary b sits on merge diagonal d = min(b*TILE, rows+nnz); r = the row the diagonal cuts
+//   (largest r with r + off[r] <= d).  Rows shorter than LONG_ROW are never cut: the boundary moves to
+//   the row start (r, off[r]); long rows are cut exactly at the diagonal (r, off[r] + e).
+// ------------------------------------------------------------------------------------------------
+__global__ void csr_partition_kernel(const int* __restrict__ off, int base, int64_t rows, int64_t nnz,
+                                     int64_t num_tiles, PlanView plan) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > num_tiles) return;
+    int64_t d = b * CSR_TILE_ITEMS;
+    if (d > rows + nnz) d = rows + nnz;
+    int64_t lo = 0, hi = rows;
+    while (lo < hi) {
+        int64_t mid = (lo + hi + 1) >> 1;
+        if (mid + (int64_t)(off[mid] - base) <= d) lo = mid; else hi = mid - 1;
+    }
+    int64_t r = lo, n = off[r] - base;
+    if (r < rows) {
+        int64_t len = (int64_t)(off[r + 1] - base) - n;
+        int64_t e = d - (r + n);
+        if (len >= CSR_LONG_ROW && e > 0) n += e;
+    }
+    plan.tiles[b] = make_int2((int)r, (int)n);
+    plan.counters[b] = 0;
+    plan.head_part[b] = 0.0;
+    plan.tail_part[b] = 0.0;
+}
+
+template <typename T>
+struct CsrArgs {
+    const int* off;
+    const int* col;
+    const T*   val;
+    const T*   x;
+    T*         y;
+    int        base;
+    int        rows;
+    int        nnz;
+    int        vec_ok;  // val/col 16-byte aligned -> 128-bit streaming loads
+    Scalars<T> s;
+    PlanView   plan;
+};
+
+// Sum sP[lo, hi) with the whole CTA, fixed order (bit-reproducible). Result valid on thread 0.
+template <typename T, int BLOCK>
+__device__ __forceinline__ T block_sum_range(const T* sP, int lo, int hi, T* sRed) {
+    T s = T(0);
+    for (int k = lo + (int)threadIdx.x; k < hi; k += BLOCK) s += sP[k];
+    s = warp_sum(s);
+    __syncthreads();  // sRed reuse
+    if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5] = s;
+    __syncthreads();
+    T tot = T(0);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < BLOCK / 32; w++) tot += sRed[w];
+    }
+    return tot;
+}
+
+// Rows [r_first, r_first + nrows) are complete inside the tile; products of non-zero j live at sP[j - ns].
+template <typename T, int G, int BLOCK>
+__device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, int r_first, int nrows, int ns,
+                                            T alpha, T beta) {
+    constexpr int GROUPS = BLOCK / G;
+    const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+    for (int r0 = 0; r0 < nrows; r0 += GROUPS) {
+        const int  ri = r0 + gid;
+        const bool active = ri < nrows;
+        T sum = T(0);
+        if (active) {
+            const int r = r_first + ri;
+            const int s = __ldg(a.off + r) - a.base - ns, e = __ldg(a.off + r + 1) - a.base - ns;
+            for (int k = s + gl; k < e; k += G) sum += sP[k];
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, G);
+        if (active && gl == 0) {
+            T* yp = a.y + r_first + ri;
+            *yp = axpby(alpha, sum, beta, yp);
+        }
+    }
+}
+
+// A split row R is covered by tiles b1 .. b2 (b1 holds its start as a "tail", the others hold "heads").
+// Every covering tile deposits its partial and bumps counter[b1]; the last one to arrive adds the
+// partials in tile order and writes y[R].  The counter is left at 0 for the next launch.
+template <typename T>
+__device__ __forceinline__ void split_row_arrive(const CsrArgs<T>& a, int R, T alpha, T beta) {
+    const int64_t g0 = (int64_t)R + (__ldg(a.off + R) - a.base);
+    const int64_t g1 = (int64_t)R + (__ldg(a.off + R + 1) - a.base);
+    const int b1 = (int)(g0 / CSR_TILE_ITEMS), b2 = (int)(g1 / CSR_TILE_ITEMS);
+    const int expected = b2 - b1 + 1;
+    __threadfence();
+    const int old = atomicAdd(a.plan.counters + b1, 1);
+    if (old == expected - 1) {
+        __threadfence();
+        double s = __ldcg(a.plan.tail_part + b1);
+        for (int b = b1 + 1; b <= b2; b++) s += __ldcg(a.plan.head_part + b);
+        a.plan.counters[b1] = 0;
+        T* yp = a.y + R;
+        *yp = axpby(alpha, (T)s, beta, yp);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CSR_BLOCK) csr_tile_kernel(const CsrArgs<T> a) {
+    __shared__ T sP[CSR_SMEM_ELEMS];
+    __shared__ T sRed[CSR_BLOCK / 32];
+
+    const int  b  = blockIdx.x;
+    const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
+    const int  rs = st.x, ns = st.y, re = en.x, ne = en.y;
+    const T alpha = a.s.a(), beta = a.s.b();
+
+    // ---------------- phase 1: stream val/col, gather x, park products in shared memory -------------
+    {
+        const int al = ns & ~(CSR_VEC - 1);
+        const int nnz_vec_end = a.vec_ok ? (a.nnz & ~(CSR_VEC - 1)) : 0;  // below this, 4-wide loads are in bounds
+        int c[CSR_ITERS][CSR_VEC];
+        T   v[CSR_ITERS][CSR_VEC];
+#pragma unroll
+        for (int it = 0; it < CSR_ITERS; it++) {
+            const int i0 = al + (it * CSR_BLOCK + (int)threadIdx.x) * CSR_VEC;
+            if (i0 < ne) {
+                if (i0 + CSR_VEC <= nnz_vec_end) {
+                    const int4 cc = ldg_stream_int4(a.col + i0);
+                    c[it][0] = cc.x; c[it][1] = cc.y; c[it][2] = cc.z; c[it][3] = cc.w;
+                    load4_stream(a.val + i0, v[it]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CSR_VEC; j++) {
+                        const bool ok = i0 + j < a.nnz;
+                        c[it][j] = ok ? ldg_stream(a.col + i0 + j) : a.base;
+                        v[it][j] = ok ? ldg_stream(a.val + i0 + j) : T(0);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < CSR_ITERS; it++) {
+            const int i0 = al + (it * CSR_BLOCK + (int)threadIdx.x) * CSR_VEC;
+            if (i0 < ne) {
+                T xv[CSR_VEC];
+#pragma unroll
+                for (int j = 0; j < CSR_VEC; j++) {
+                    const int i = i0 + j;
+                    xv[j] = (i >= ns && i < ne) ? __ldg(a.x + (c[it][j] - a.base)) : T(0);
+                }
+#pragma unroll
+                for (int j = 0; j < CSR_VEC; j++) {
+                    const int i = i0 + j;
+                    if (i >= ns && i < ne) sP[i - ns] = v[it][j] * xv[j];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: per-row reduction out of shared memory ------------------------------
+    const int cnt = ne - ns;
+    bool head = false;
+    int  head_end = 0;  // products [0, head_end) belong to the split row rs
+    if (rs < a.rows) {
+        const int o0 = __ldg(a.off + rs) - a.base;
+        if (ns > o0) {
+            head = true;
+            const int o1 = __ldg(a.off + rs + 1) - a.base;
+            head_end = (o1 < ne ? o1 : ne) - ns;
+        }
+    }
+    const int r_first = rs + (head ? 1 : 0);
+    const int nrows   = re - r_first;  // complete rows (may be <= 0)
+    int  tail_beg = cnt;               // products [tail_beg, cnt) belong to the split row re
+    bool tail = false;
+    if (re < a.rows && re >= r_first) {
+        const int o0 = __ldg(a.off + re) - a.base;
+        if (ne > o0) { tail = true; tail_beg = o0 - ns; }
+    }
+
+    if (nrows > 0) {
+        const int body = tail_beg - head_end;
+        const int avg2 = body / (2 * nrows);  // half the mean row length
+        if      (avg2 <= 1)  reduce_rows<T, 1,  CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
+        else if (avg2 <= 2)  reduce_rows<T, 2,  CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
+        else if (avg2 <= 4)  reduce_rows<T, 4,  CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
+        else if (avg2 <= 8)  reduce_rows<T, 8,  CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
+        else if (avg2 <= 16) reduce_rows<T, 16, CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
+        else                 reduce_rows<T, 32, CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
+    }
+
+    if (head) {  // block-uniform
+        const T hs = block_sum_range<T, CSR_BLOCK>(sP, 0, head_end, sRed);
+        if (threadIdx.x == 0) {
+            a.plan.head_part[b] = (double)hs;
+            split_row_arrive(a, rs, alpha, beta);
+        }
+    }
+    if (tail) {  // block-uniform
+        const T ts = block_sum_range<T, CSR_BLOCK>(sP, tail_beg, cnt, sRed);
+        if (threadIdx.x == 0) {
+            a.plan.tail_part[b] = (double)ts;
+            split_row_arrive(a, re, alpha, beta);
+        }
+    }
+}
+
+template <typename T>
+static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void* off, const void* col,
+                      const void* val, int base, const void* alpha, const void* beta, int on_device,
+                      const void* x, void* y, void* ws) {
+    const int64_t nt = csr_num_tiles(rows, nnz);
+    if (nt == 0) return 0;
+    CsrArgs<T> a;
+    a.off = (const int*)off; a.col = (const int*)col; a.val = (const T*)val;
+    a.x = (const T*)x; a.y = (T*)y; a.base = base; a.rows = (int)rows; a.nnz = (int)nnz;
+    a.vec_ok = (((uintptr_t)col | (uintptr_t)val) & 15) == 0;
+    if (on_device) { a.s.alpha = T(0); a.s.beta = T(0); a.s.alpha_dev = (const T*)alpha; a.s.beta_dev = (const T*)beta; }
+    else { a.s.alpha = *(const T*)alpha; a.s.beta = *(const T*)beta; a.s.alpha_dev = nullptr; a.s.beta_dev = nullptr; }
+    plan_layout(nt, ws, &a.plan);
+    csr_tile_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+size_t b200spmv_csr_workspace_bytes(int64_t rows, int64_t nnz) {
+    if (rows < 0 || nnz < 0) return 0;
+    return plan_layout(csr_num_tiles(rows, nnz), nullptr, nullptr);
+}
+
+int64_t b200spmv_csr_num_tiles(int64_t rows, int64_t nnz) { return csr_num_tiles(rows, nnz); }
+
+void b200spmv_csr_plan_params(int32_t* tile_items, int32_t* long_row, int32_t* block_threads) {
+    if (tile_items) *tile_items = CSR_TILE_ITEMS;
+    if (long_row) *long_row = CSR_LONG_ROW;
+    if (block_threads) *block_threads = CSR_BLOCK;
+}
+
+size_t b200spmv_csr_plan_tiles_offset(void) { return PLAN_HEADER_BYTES; }
+
+int b200spmv_csr_analyze(void* stream, int64_t rows, int64_t nnz, const void* row_offsets, int32_t base,
+                         void* workspace) {
+    if (rows < 0 || nnz < 0 || rows > INT32_MAX - 1 || nnz > INT32_MAX - 1 || !workspace || (rows > 0 && !row_offsets))
+        return -1;
+    const int64_t nt = csr_num_tiles(rows, nnz);
+    PlanView v;
+    plan_layout(nt, workspace, &v);
+    if (rows == 0) return 0;  // (the first PLAN_HEADER_BYTES of the workspace are reserved, unused on device)
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((nt + 1 + threads - 1) / threads);
+    csr_partition_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((const int*)row_offsets, base, rows, nnz, nt, v);
+    return (int)cudaGetLastError();
+}
+
+int b200spmv_csr_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz, const void* row_offsets,
+                    const void* col_ind, const void* values, int32_t base, const void* alpha, const void* beta,
+                    int scalars_on_device, const void* x, void* y, void* workspace) {
+    if (rows < 0 || cols < 0 || nnz < 0 || !alpha || !beta) return -1;
+    if (rows == 0) return 0;
+    if (!row_offsets || !y || !workspace || (nnz > 0 && (!col_ind || !values || !x))) return -1;
+    if (dtype == 0)
+        return launch_csr<float>((cudaStream_t)stream, rows, nnz, row_offsets, col_ind, values, base, alpha, beta,
+                                 scalars_on_device, x, y, workspace);
+    if (dtype == 1)
+        return launch_csr<double>((cudaStream_t)stream, rows, nnz, row_offsets, col_ind, values, base, alpha, beta,
+                                  scalars_on_device, x, y, workspace);
+    return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,228 @@
+"""Host-side mirror of the cuSPARSE generic API that the reference samples call for SpMV.
+
+Same names, argument order and error behaviour as the C calls in cuSPARSE/spmv_csr/spmv_csr_example.c:86-118
+(cusparseCreate ... cusparseCreateCsr ... cusparseSpMV_bufferSize/_preprocess/cusparseSpMV ... cusparseDestroy*), so
+the parity tests read like the reference's own samples.  Every call goes through the C ABI:
+
+  impl="b200"      descriptor + SpMV symbols come from libb200spmv.so (the product: sm_100a kernels)
+  impl="cusparse"  the same symbols come from the closed libcusparse.so.12 (the GPU oracle)
+
+Handle management (cusparseCreate/Destroy/SetStream/SetPointerMode) always belongs to the real library, exactly as
+when a sample is linked with `-lb200spmv -lcusparse`.  torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as _lib
+
+# enums (cusparse.h:260-278, 4988-5007, 5669-5676; library_types.h)
+CUSPARSE_STATUS_SUCCESS = 0
+CUSPARSE_STATUS_INVALID_VALUE = 3
+CUSPARSE_STATUS_NOT_SUPPORTED = 10
+CUSPARSE_OPERATION_NON_TRANSPOSE = 0
+CUSPARSE_OPERATION_TRANSPOSE = 1
+CUSPARSE_INDEX_32I = 2
+CUSPARSE_INDEX_64I = 3
+CUSPARSE_INDEX_BASE_ZERO = 0
+CUSPARSE_INDEX_BASE_ONE = 1
+CUSPARSE_POINTER_MODE_HOST = 0
+CUSPARSE_POINTER_MODE_DEVICE = 1
+CUSPARSE_SPMV_ALG_DEFAULT = 0
+CUSPARSE_SPMV_COO_ALG1 = 1
+CUSPARSE_SPMV_CSR_ALG1 = 2
+CUSPARSE_SPMV_CSR_ALG2 = 3
+CUSPARSE_SPMV_COO_ALG2 = 4
+CUSPARSE_SPMV_SELL_ALG1 = 5
+CUDA_R_32F = 0
+CUDA_R_64F = 1
+
+_VT = {torch.float32: CUDA_R_32F, torch.float64: CUDA_R_64F}
+_IT = {torch.int32: CUSPARSE_INDEX_32I, torch.int64: CUSPARSE_INDEX_64I}
+_CT = {torch.float32: C.c_float, torch.float64: C.c_double}
+
+
+class CuSparseError(RuntimeError):
+    """Raised where the samples' CHECK_CUSPARSE macro would print and exit (spmv_csr_example.c:33-41)."""
+
+    def __init__(self, fn, status):
+        super().__init__(f"{fn} failed with cusparseStatus_t {status}")
+        self.status = status
+
+
+def _ptr(t):
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(int(t))
+
+
+class Api:
+    """One instance per implementation under test."""
+
+    def __init__(self, impl: str = "b200"):
+        if impl not in ("b200", "cusparse"):
+            raise ValueError(impl)
+        self.impl = impl
+        self.real = _lib.real()
+        self.lib = _lib.shim() if impl == "b200" else self.real
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _call(self, lib, name, *args):
+        st = getattr(lib, name)(*args)
+        if st != CUSPARSE_STATUS_SUCCESS:
+            raise CuSparseError(name, st)
+
+    # ---- handle (always the real library) ----------------------------------------------------------
+    def cusparseCreate(self):
+        h = C.c_void_p()
+        self._call(self.real, "cusparseCreate", C.byref(h))
+        self.cusparseSetStream(h, torch.cuda.current_stream().cuda_stream)
+        return h
+
+    def cusparseDestroy(self, h):
+        self._call(self.real, "cusparseDestroy", h)
+
+    def cusparseSetStream(self, h, stream):
+        self._call(self.real, "cusparseSetStream", h, C.c_void_p(int(stream)))
+
+    def cusparseSetPointerMode(self, h, mode):
+        self._call(self.real, "cusparseSetPointerMode", h, C.c_int(mode))
+
+    # ---- descriptors -------------------------------------------------------------------------------
+    def cusparseCreateCsr(self, rows, cols, nnz, csrRowOffsets, csrColInd, csrValues, idxBase=CUSPARSE_INDEX_BASE_ZERO):
+        d = C.c_void_p()
+        self._call(self.lib, "cusparseCreateCsr", C.byref(d), C.c_int64(rows), C.c_int64(cols), C.c_int64(nnz),
+                   _ptr(csrRowOffsets), _ptr(csrColInd), _ptr(csrValues), C.c_int(_IT[csrRowOffsets.dtype]),
+                   C.c_int(_IT[csrColInd.dtype]), C.c_int(idxBase), C.c_int(_VT[csrValues.dtype]))
+        return d
+
+    def cusparseCreateCoo(self, rows, cols, nnz, cooRowInd, cooColInd, cooValues, idxBase=CUSPARSE_INDEX_BASE_ZERO):
+        d = C.c_void_p()
+        self._call(self.lib, "cusparseCreateCoo", C.byref(d), C.c_int64(rows), C.c_int64(cols), C.c_int64(nnz),
+                   _ptr(cooRowInd), _ptr(cooColInd), _ptr(cooValues), C.c_int(_IT[cooRowInd.dtype]), C.c_int(idxBase),
+                   C.c_int(_VT[cooValues.dtype]))
+        return d
+
+    def cusparseCreateSlicedEll(self, rows, cols, nnz, sellValuesSize, sliceSize, sellSliceOffsets, sellColInd, sellValues,
+                                idxBase=CUSPARSE_INDEX_BASE_ZERO):
+        d = C.c_void_p()
+        self._call(self.lib, "cusparseCreateSlicedEll", C.byref(d), C.c_int64(rows), C.c_int64(cols), C.c_int64(nnz),
+                   C.c_int64(sellValuesSize), C.c_int64(sliceSize), _ptr(sellSliceOffsets), _ptr(sellColInd),
+                   _ptr(sellValues), C.c_int(_IT[sellSliceOffsets.dtype]), C.c_int(_IT[sellColInd.dtype]),
+                   C.c_int(idxBase), C.c_int(_VT[sellValues.dtype]))
+        return d
+
+    def cusparseDestroySpMat(self, d):
+        self._call(self.lib, "cusparseDestroySpMat", d)
+
+    def cusparseCreateDnVec(self, size, values):
+        d = C.c_void_p()
+        self._call(self.lib, "cusparseCreateDnVec", C.byref(d), C.c_int64(size), _ptr(values), C.c_int(_VT[values.dtype]))
+        return d
+
+    def cusparseDestroyDnVec(self, d):
+        self._call(self.lib, "cusparseDestroyDnVec", d)
+
+    def cusparseDnVecSetValues(self, d, values):
+        self._call(self.lib, "cusparseDnVecSetValues", d, _ptr(values))
+
+    def cusparseCsrSetPointers(self, d, off, col, val):
+        self._call(self.lib, "cusparseCsrSetPointers", d, _ptr(off), _ptr(col), _ptr(val))
+
+    # ---- SpMV --------------------------------------------------------------------------------------
+    @staticmethod
+    def _scalar(v, dtype):
+        """alpha/beta: python number -> host scalar of the compute type; torch tensor -> device pointer."""
+        if isinstance(v, torch.Tensor):
+            return C.c_void_p(v.data_ptr()), v
+        c = _CT[dtype](v)
+        return C.cast(C.pointer(c), C.c_void_p), c
+
+    def cusparseSpMV_bufferSize(self, handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg=CUSPARSE_SPMV_ALG_DEFAULT):
+        dt = torch.float32 if computeType == CUDA_R_32F else torch.float64
+        pa, _ka = self._scalar(alpha, dt)
+        pb, _kb = self._scalar(beta, dt)
+        size = C.c_size_t(0)
+        self._call(self.lib, "cusparseSpMV_bufferSize", handle, C.c_int(opA), pa, matA, vecX, pb, vecY, C.c_int(computeType),
+                   C.c_int(alg), C.byref(size))
+        return int(size.value)
+
+    def cusparseSpMV_preprocess(self, handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer):
+        dt = torch.float32 if computeType == CUDA_R_32F else torch.float64
+        pa, _ka = self._scalar(alpha, dt)
+        pb, _kb = self._scalar(beta, dt)
+        self._call(self.lib, "cusparseSpMV_preprocess", handle, C.c_int(opA), pa, matA, vecX, pb, vecY, C.c_int(computeType),
+                   C.c_int(alg), _ptr(externalBuffer))
+
+    def cusparseSpMV(self, handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer):
+        dt = torch.float32 if computeType == CUDA_R_32F else torch.float64
+        pa, _ka = self._scalar(alpha, dt)
+        pb, _kb = self._scalar(beta, dt)
+        self._call(self.lib, "cusparseSpMV", handle, C.c_int(opA), pa, matA, vecX, pb, vecY, C.c_int(computeType),
+                   C.c_int(alg), _ptr(externalBuffer))
+
+
+class SpMVOperator:
+    """The sample's call sequence packaged once: descriptors + external buffer live as long as the operator
+    (cg_example.c:387-418 keeps matA / d_bufferMV for the whole solve and calls cusparseSpMV per iteration)."""
+
+    def __init__(self, api: Api, fmt: str, rows: int, cols: int, arrays: dict, base: int = 0, preprocess: bool = True,
+                 alg: int = CUSPARSE_SPMV_ALG_DEFAULT, handle=None):
+        self.api, self.fmt, self.rows, self.cols, self.base, self.alg = api, fmt, rows, cols, base, alg
+        self.arrays = arrays  # keeps the device tensors alive
+        self.own_handle = handle is None
+        self.handle = api.cusparseCreate() if handle is None else handle
+        val = arrays["val"]
+        self.dtype = val.dtype
+        self.ctype = _VT[val.dtype]
+        if fmt == "csr":
+            self.nnz = int(arrays["col"].numel())
+            self.mat = api.cusparseCreateCsr(rows, cols, self.nnz, arrays["off"], arrays["col"], val, base)
+        elif fmt == "coo":
+            self.nnz = int(arrays["col"].numel())
+            self.mat = api.cusparseCreateCoo(rows, cols, self.nnz, arrays["row"], arrays["col"], val, base)
+        elif fmt == "sell":
+            self.nnz = int(arrays["nnz"])
+            self.mat = api.cusparseCreateSlicedEll(rows, cols, self.nnz, int(val.numel()), int(arrays["slice_size"]),
+                                                   arrays["off"], arrays["col"], val, base)
+        else:
+            raise ValueError(fmt)
+        self._x = torch.empty(max(cols, 1), dtype=val.dtype, device=val.device)
+        self._y = torch.empty(max(rows, 1), dtype=val.dtype, device=val.device)
+        self.vecX = api.cusparseCreateDnVec(cols, self._x)
+        self.vecY = api.cusparseCreateDnVec(rows, self._y)
+        size = api.cusparseSpMV_bufferSize(self.handle, CUSPARSE_OPERATION_NON_TRANSPOSE, 1.0, self.mat, self.vecX, 0.0,
+                                           self.vecY, self.ctype, alg)
+        self.buffer_bytes = size
+        self.buffer = torch.empty(max(size, 16), dtype=torch.uint8, device=val.device)
+        if preprocess:
+            api.cusparseSpMV_preprocess(self.handle, CUSPARSE_OPERATION_NON_TRANSPOSE, 1.0, self.mat, self.vecX, 0.0,
+                                        self.vecY, self.ctype, alg, self.buffer)
+
+    def __call__(self, x: torch.Tensor, y: torch.Tensor, alpha=1.0, beta=0.0):
+        """y = alpha*A*x + beta*y, asynchronous on the handle's stream."""
+        a = self.api
+        a.cusparseDnVecSetValues(self.vecX, x)
+        a.cusparseDnVecSetValues(self.vecY, y)
+        a.cusparseSpMV(self.handle, CUSPARSE_OPERATION_NON_TRANSPOSE, alpha, self.mat, self.vecX, beta, self.vecY, self.ctype,
+                       self.alg, self.buffer)
+        return y
+
+    def close(self):
+        if self.mat is not None:
+            self.api.cusparseDestroySpMat(self.mat)
+            self.api.cusparseDestroyDnVec(self.vecX)
+            self.api.cusparseDestroyDnVec(self.vecY)
+            if self.own_handle:
+                self.api.cusparseDestroy(self.handle)
+            self.mat = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

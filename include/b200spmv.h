@@ -1,0 +1,158 @@
+/*
+ * b200spmv.h -- C ABI of libb200spmv.so, the B200-native (sm_100a) drop-in for the cusparseSpMV path
+ * of NVIDIA/CUDALibrarySamples (cuSPARSE/spmv_csr, spmv_coo, spmv_sell, cg, bicgstab).
+ *
+ * Two layers, both `extern "C"`, plain pointers and sizes only:
+ *
+ *   1. The cuSPARSE generic-API symbols the samples call.  The shim re-exports them with the exact
+ *      prototypes of the CUDA 12.9 toolkit header the samples include
+ *      (cuSPARSE/spmv_csr/spmv_csr_example.c:19 `#include <cusparse.h>`); every other cusparse* symbol
+ *      keeps resolving to the real libcusparse.so.12 (link order `-lb200spmv -lcusparse`, or LD_PRELOAD).
+ *
+ *   2. The native entry points underneath (b200spmv_*): descriptor-free, usable without libcusparse.
+ *
+ * Every function the library exports is tagged B200SPMV_EXPORT; tests/test_abi.py greps this header for
+ * the tag and checks that each symbol is present in the built .so.
+ */
+#ifndef B200SPMV_H_
+#define B200SPMV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#define B200SPMV_EXPORT /* exported from libb200spmv.so */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ============================================================================================== *
+ * Layer 2: native entry points.                                                                   *
+ *   stream    : cudaStream_t (passed as void*); all work is enqueued asynchronously on it, no     *
+ *               host synchronisation, no allocation -> CUDA-graph capturable.                     *
+ *   dtype     : 0 = fp32 (== CUDA_R_32F), 1 = fp64 (== CUDA_R_64F); A, x, y and the arithmetic    *
+ *               all use this type.  Indices are int32.  base is 0 or 1.                           *
+ *   alpha/beta: pointers to one value of `dtype`; host memory when scalars_on_device == 0,        *
+ *               device memory (read inside the kernel) otherwise.                                 *
+ *   return    : 0 on success, -1 on invalid arguments, otherwise the cudaError_t of the launch.   *
+ * ============================================================================================== */
+
+/* CSR.  The workspace holds the structure-only tile partition ("plan") built by _analyze:
+ * replaces cusparseSpMV_bufferSize / cusparseSpMV_preprocess / cusparseSpMV for
+ * cusparseCreateCsr descriptors (cuSPARSE/spmv_csr/spmv_csr_example.c:97-112,
+ * cuSPARSE/cg/cg_example.c:409-418,156-160,220-224,294-297). */
+B200SPMV_EXPORT size_t b200spmv_csr_workspace_bytes(int64_t rows, int64_t nnz);
+B200SPMV_EXPORT int    b200spmv_csr_analyze(void* stream, int64_t rows, int64_t nnz, const void* row_offsets,
+                                            int32_t base, void* workspace);
+B200SPMV_EXPORT int    b200spmv_csr_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz,
+                                       const void* row_offsets, const void* col_ind, const void* values,
+                                       int32_t base, const void* alpha, const void* beta, int scalars_on_device,
+                                       const void* x, void* y, void* workspace);
+/* Introspection used by the parity tests (bit-exact integer preprocessing): number of tiles, and the
+ * constants the partition was built with. */
+B200SPMV_EXPORT int64_t b200spmv_csr_num_tiles(int64_t rows, int64_t nnz);
+B200SPMV_EXPORT void    b200spmv_csr_plan_params(int32_t* tile_items, int32_t* long_row, int32_t* block_threads);
+B200SPMV_EXPORT size_t  b200spmv_csr_plan_tiles_offset(void);
+
+/* COO (row-sorted or not).  Replaces cusparseSpMV for cusparseCreateCoo descriptors
+ * (cuSPARSE/spmv_coo/spmv_coo_example.c:86-104). */
+B200SPMV_EXPORT size_t b200spmv_coo_workspace_bytes(int64_t rows, int64_t nnz);
+B200SPMV_EXPORT int    b200spmv_coo_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz,
+                                       const void* row_ind, const void* col_ind, const void* values,
+                                       int32_t base, const void* alpha, const void* beta, int scalars_on_device,
+                                       const void* x, void* y, void* workspace);
+
+/* Sliced-ELL.  Replaces cusparseSpMV for cusparseCreateSlicedEll descriptors
+ * (cuSPARSE/spmv_sell/spmv_sell_example.c:103-122).  Padding entries have column index -1 (+base). */
+B200SPMV_EXPORT size_t b200spmv_sell_workspace_bytes(int64_t rows, int64_t sell_values_size, int64_t slice_size);
+B200SPMV_EXPORT int    b200spmv_sell_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t slice_size,
+                                        const void* slice_offsets, const void* col_ind, const void* values,
+                                        int32_t base, const void* alpha, const void* beta, int scalars_on_device,
+                                        const void* x, void* y, void* workspace);
+
+/* Synthetic-workload generators on the device (bench / tests plumbing; bit-identical to oracle/spmv_oracle.c). */
+B200SPMV_EXPORT int b200gen_rmat_keys(void* stream, uint64_t seed, int64_t e0, int64_t count, int32_t scale,
+                                      uint64_t tA, uint64_t tAB, uint64_t tABC, int64_t rows, int64_t cols,
+                                      int64_t* keys_out);
+B200SPMV_EXPORT int b200gen_uniform(void* stream, int dtype, uint64_t seed, int64_t i0, int64_t count, void* out);
+B200SPMV_EXPORT int b200gen_stencil5_counts(void* stream, int32_t grid, int32_t* counts_out);
+B200SPMV_EXPORT int b200gen_stencil5_fill(void* stream, int32_t grid, double mass, double ux, double uy,
+                                          const int32_t* row_offsets, int32_t* col_out, double* val_out);
+B200SPMV_EXPORT int b200gen_laplace7_counts(void* stream, int32_t nx, int32_t* counts_out);
+B200SPMV_EXPORT int b200gen_laplace7_fill(void* stream, int dtype, int32_t nx, const int32_t* row_offsets,
+                                          int32_t* col_out, void* val_out);
+
+B200SPMV_EXPORT const char* b200spmv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+/* ============================================================================================== *
+ * Layer 1: the cuSPARSE symbols re-exported by the shim (prototypes == /usr/local/cuda/include/   *
+ * cusparse.h of CUDA 12.9; the line numbers cite that header, the call sites cite the reference). *
+ * Compile with -DB200SPMV_DECLARE_CUSPARSE (and cusparse.h on the include path) to see them.      *
+ * ============================================================================================== */
+#ifdef B200SPMV_DECLARE_CUSPARSE
+#include <cusparse.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* cusparse.h:5208 -- spmv_csr_example.c:88-91, cg_example.c:387-395, bicgstab_example.c:465-484 */
+B200SPMV_EXPORT cusparseStatus_t cusparseCreateCsr(cusparseSpMatDescr_t*, int64_t, int64_t, int64_t, void*, void*, void*,
+                                                   cusparseIndexType_t, cusparseIndexType_t, cusparseIndexBase_t, cudaDataType);
+/* cusparse.h:5221 -- cuSOLVERSp2cuDSS/csreigvsi2cuDSS_double.cpp:139-141 */
+B200SPMV_EXPORT cusparseStatus_t cusparseCreateConstCsr(cusparseConstSpMatDescr_t*, int64_t, int64_t, int64_t, const void*,
+                                                        const void*, const void*, cusparseIndexType_t, cusparseIndexType_t,
+                                                        cusparseIndexBase_t, cudaDataType);
+/* cusparse.h:5362 -- spmv_coo_example.c:86-89 */
+B200SPMV_EXPORT cusparseStatus_t cusparseCreateCoo(cusparseSpMatDescr_t*, int64_t, int64_t, int64_t, void*, void*, void*,
+                                                   cusparseIndexType_t, cusparseIndexBase_t, cudaDataType);
+/* cusparse.h:5374 */
+B200SPMV_EXPORT cusparseStatus_t cusparseCreateConstCoo(cusparseConstSpMatDescr_t*, int64_t, int64_t, int64_t, const void*,
+                                                        const void*, const void*, cusparseIndexType_t, cusparseIndexBase_t,
+                                                        cudaDataType);
+/* cusparse.h:5470 -- spmv_sell_example.c:103-107 */
+B200SPMV_EXPORT cusparseStatus_t cusparseCreateSlicedEll(cusparseSpMatDescr_t*, int64_t, int64_t, int64_t, int64_t, int64_t,
+                                                         void*, void*, void*, cusparseIndexType_t, cusparseIndexType_t,
+                                                         cusparseIndexBase_t, cudaDataType);
+/* cusparse.h:5485 */
+B200SPMV_EXPORT cusparseStatus_t cusparseCreateConstSlicedEll(cusparseConstSpMatDescr_t*, int64_t, int64_t, int64_t, int64_t,
+                                                              int64_t, const void*, const void*, const void*,
+                                                              cusparseIndexType_t, cusparseIndexType_t, cusparseIndexBase_t,
+                                                              cudaDataType);
+/* cusparse.h:5137 -- spmv_csr_example.c:115 */
+B200SPMV_EXPORT cusparseStatus_t cusparseDestroySpMat(cusparseConstSpMatDescr_t);
+/* cusparse.h:5312 / 5410 / 5156: keep the side table coherent when pointers are swapped */
+B200SPMV_EXPORT cusparseStatus_t cusparseCsrSetPointers(cusparseSpMatDescr_t, void*, void*, void*);
+B200SPMV_EXPORT cusparseStatus_t cusparseCooSetPointers(cusparseSpMatDescr_t, void*, void*, void*);
+B200SPMV_EXPORT cusparseStatus_t cusparseSpMatSetValues(cusparseSpMatDescr_t, void*);
+/* cusparse.h:5094 / 5100 / 5106 / 5129 -- spmv_csr_example.c:93-95,116-117, cg_example.c:371-378 */
+B200SPMV_EXPORT cusparseStatus_t cusparseCreateDnVec(cusparseDnVecDescr_t*, int64_t, void*, cudaDataType);
+B200SPMV_EXPORT cusparseStatus_t cusparseCreateConstDnVec(cusparseConstDnVecDescr_t*, int64_t, const void*, cudaDataType);
+B200SPMV_EXPORT cusparseStatus_t cusparseDestroyDnVec(cusparseConstDnVecDescr_t);
+B200SPMV_EXPORT cusparseStatus_t cusparseDnVecSetValues(cusparseDnVecDescr_t, void*);
+/* cusparse.h:5691 -- spmv_csr_example.c:97-100, cg_example.c:409-412 */
+B200SPMV_EXPORT cusparseStatus_t cusparseSpMV_bufferSize(cusparseHandle_t, cusparseOperation_t, const void*,
+                                                         cusparseConstSpMatDescr_t, cusparseConstDnVecDescr_t, const void*,
+                                                         cusparseDnVecDescr_t, cudaDataType, cusparseSpMVAlg_t, size_t*);
+/* cusparse.h:5703 -- spmv_csr_example.c:104-107, csreigvsi2cuDSS_double.cpp:148-150 */
+B200SPMV_EXPORT cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t, cusparseOperation_t, const void*,
+                                                         cusparseConstSpMatDescr_t, cusparseConstDnVecDescr_t, const void*,
+                                                         cusparseDnVecDescr_t, cudaDataType, cusparseSpMVAlg_t, void*);
+/* cusparse.h:5679 -- spmv_csr_example.c:110-112, cg_example.c:156,220,294,415,
+ *                    bicgstab_example.c:190,262,315,358,504 */
+B200SPMV_EXPORT cusparseStatus_t cusparseSpMV(cusparseHandle_t, cusparseOperation_t, const void*, cusparseConstSpMatDescr_t,
+                                              cusparseConstDnVecDescr_t, const void*, cusparseDnVecDescr_t, cudaDataType,
+                                              cusparseSpMVAlg_t, void*);
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPMV_DECLARE_CUSPARSE */
+
+/* Shim behaviour switches (environment, read once at first use):
+ *   B200SPMV_FORWARD=1   cusparseSpMV* forward to the real libcusparse (A/B oracle runs, same binary)
+ *   B200SPMV_LOG=1       one line per call on stderr naming the path taken
+ *   B200SPMV_CUSPARSE=/path/to/libcusparse.so.12   which real library to dlopen
+ */
+#endif /* B200SPMV_H_ */

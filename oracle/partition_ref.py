@@ -1,0 +1,61 @@
+"""oracle/partition_ref.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+numpy restatement of the integer preprocessing that cusparseSpMV_preprocess performs in this build
+(b200::csr_partition_kernel in cudalibrarysamples_b200/csrc/spmv_csr.cu): the tile partition of the CSR
+(rows + nnz) merge list.  The reference's own preprocessing (cusparse::partition_kernel in the closed
+libcusparse) is not observable, so parity for this integer work is defined against this restatement:
+tests/test_parity_gpu.py demands bit-exact equality of every (row, nnz) tile coordinate.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def csr_partition(off, base, tile_items, long_row):
+    """Returns int32 array [num_tiles+1, 2] of (row, nnz) tile start coordinates.
+
+    boundary b sits on merge diagonal d = min(b*tile_items, rows+nnz); r = largest row index with
+    r + off[r] <= d.  Rows shorter than long_row are never cut (boundary = row start); longer rows are cut
+    exactly at the diagonal.
+    """
+    off = np.asarray(off, np.int64) - base
+    rows = off.size - 1
+    nnz = int(off[-1])
+    num_tiles = (rows + nnz + tile_items - 1) // tile_items
+    d = np.minimum(np.arange(num_tiles + 1, dtype=np.int64) * tile_items, rows + nnz)
+    g = np.arange(rows + 1, dtype=np.int64) + off          # strictly increasing
+    r = np.searchsorted(g, d, side="right") - 1            # largest r with g[r] <= d
+    n = off[r].copy()
+    inside = r < rows
+    rr = np.where(inside, r, 0)
+    length = np.where(inside, off[np.minimum(rr + 1, rows)] - off[rr], 0)
+    e = d - (r + n)
+    cut = inside & (length >= long_row) & (e > 0)
+    n = np.where(cut, n + e, n)
+    return np.stack([r, n], axis=1).astype(np.int32)
+
+
+def check_partition(tiles, off, base, tile_items, long_row):
+    """Invariants every valid partition must satisfy (used on CPU and at full size on the GPU)."""
+    off = np.asarray(off, np.int64) - base
+    rows = off.size - 1
+    nnz = int(off[-1])
+    t = tiles.astype(np.int64)
+    assert t[0, 0] == 0 and t[0, 1] == 0
+    assert t[-1, 0] == rows and t[-1, 1] == nnz
+    pos = t[:, 0] + t[:, 1]
+    assert np.all(np.diff(pos) >= 0)
+    assert np.all(np.diff(t[:, 0]) >= 0) and np.all(np.diff(t[:, 1]) >= 0)
+    # a tile never holds more items than shared memory was sized for
+    assert np.all(np.diff(pos) <= tile_items + long_row - 1)
+    # a boundary is either a row start or strictly inside a long row
+    r, n = t[:, 0], t[:, 1]
+    rs = np.minimum(r, rows)
+    start = off[rs]
+    mid = n != start
+    if mid.any():
+        rl = r[mid]
+        assert np.all(rl < rows)
+        assert np.all(off[rl + 1] - off[rl] >= long_row)
+        assert np.all((n[mid] > off[rl]) & (n[mid] <= off[rl + 1]))
+    return True

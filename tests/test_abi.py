@@ -1,0 +1,77 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/b200spmv.h declares."""
+import ctypes
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b200spmv.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    names = re.findall(r"B200SPMV_EXPORT\s+[\w\s\*]+?\b(\w+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_header_declares_the_reference_entry_points():
+    names = declared_symbols()
+    # the exact symbols the reference's SpMV samples bind
+    for n in ["cusparseCreateCsr", "cusparseCreateConstCsr", "cusparseCreateCoo", "cusparseCreateSlicedEll",
+              "cusparseCreateDnVec", "cusparseDestroySpMat", "cusparseDestroyDnVec", "cusparseSpMV_bufferSize",
+              "cusparseSpMV_preprocess", "cusparseSpMV", "cusparseCsrSetPointers", "cusparseDnVecSetValues",
+              "b200spmv_csr_mv", "b200spmv_coo_mv", "b200spmv_sell_mv", "b200spmv_csr_analyze"]:
+        assert n in names, n
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", built_lib], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [n for n in declared_symbols() if n not in exported]
+    assert not missing, missing
+
+
+def test_library_loads_without_a_gpu(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    lib.b200spmv_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.b200spmv_version()
+    lib.b200spmv_csr_workspace_bytes.restype = ctypes.c_size_t
+    lib.b200spmv_csr_num_tiles.restype = ctypes.c_int64
+    t, l, b = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    lib.b200spmv_csr_plan_params(ctypes.byref(t), ctypes.byref(l), ctypes.byref(b))
+    assert t.value > l.value > 0 and b.value % 32 == 0
+    nt = lib.b200spmv_csr_num_tiles(ctypes.c_int64(1000), ctypes.c_int64(16000))
+    assert nt == (17000 + t.value - 1) // t.value
+    ws = lib.b200spmv_csr_workspace_bytes(ctypes.c_int64(1000), ctypes.c_int64(16000))
+    assert ws >= (nt + 1) * (8 + 4 + 8 + 8)
+    # argument validation happens on the host, before any CUDA call
+    assert lib.b200spmv_csr_mv(None, 7, ctypes.c_int64(4), ctypes.c_int64(4), ctypes.c_int64(9), None, None, None, 0,
+                               None, None, 0, None, None, None) == -1
+
+
+def test_sass_is_sm100a_and_streams_with_128bit_loads(built_lib):
+    sass = subprocess.check_output(["cuobjdump", "-sass", built_lib], text=True)
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    m = re.search(r"Function : \S*csr_tile_kernelId.*?(?=Function :|\Z)", sass, re.S)
+    assert m, "fp64 CSR tile kernel not found in the cubin"
+    body = m.group(0)
+    assert re.search(r"LDG\.E\.NA\.128", body)   # 128-bit, L1 no-allocate streaming loads of val[] / col_ind[]
+    assert "SHFL" in body                 # warp-shuffle row reduction
+    assert "HMMA" not in body and "UTC" not in body   # no tensor cores: HBM-bound gather-reduce
+
+
+def test_reference_samples_bind_spmv_to_the_shim():
+    """oracle/_ref/*.b200 are the unmodified reference samples linked `-lb200spmv -lcusparse` (oracle/Makefile)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "cg_example.b200")
+    if not os.path.exists(exe):
+        import pytest
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    env = dict(os.environ, LD_BIND_NOW="1", LD_DEBUG="bindings")
+    p = subprocess.run([exe], env=env, capture_output=True, text=True)
+    lines = [l for l in p.stderr.splitlines() if "cg_example.b200 [0] to" in l]
+    def target(sym):
+        return [l for l in lines if f"`{sym}'" in l][0]
+    assert "libb200spmv.so" in target("cusparseSpMV")
+    assert "libb200spmv.so" in target("cusparseCreateCsr")
+    assert "libcusparse.so.12" in target("cusparseSpSV_solve")
+    assert "libcusparse.so.12" in target("cusparseCreate")

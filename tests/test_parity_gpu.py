@@ -1,0 +1,419 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI (the cusparse* symbols exported by libb200spmv.so),
+against (i) the reference's golden vectors, (ii) the CPU oracle, (iii) the closed cusparseSpMV on the same device
+buffers, and (iv) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north_star): fp64 ||y - y_ref|| / ||y_ref|| < 1e-12, fp32 < 1e-5; integer preprocessing bit-exact.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from oracle.partition_ref import check_partition, csr_partition
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = {torch.float64: 1e-12, torch.float32: 1e-5}
+NP = {torch.float64: np.float64, torch.float32: np.float32}
+
+
+@pytest.fixture(scope="module")
+def cs():
+    from cudalibrarysamples_b200 import cusparse_api
+    return cusparse_api
+
+
+@pytest.fixture(scope="module")
+def b200(cs):
+    return cs.Api("b200")
+
+
+@pytest.fixture(scope="module")
+def closed(cs):
+    return cs.Api("cusparse")
+
+
+def dev(a):
+    return torch.as_tensor(a).cuda()
+
+
+def relerr(got, want):
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    n = np.linalg.norm(want)
+    return np.linalg.norm(got - want) / (n if n > 0 else 1.0)
+
+
+def run(cs, api, fmt, rows, cols, arrays, x, y0, alpha, beta, base=0, preprocess=True):
+    op = cs.SpMVOperator(api, fmt, rows, cols, arrays, base=base, preprocess=preprocess)
+    y = y0.clone()
+    op(x, y, alpha, beta)
+    torch.cuda.synchronize()
+    op.close()
+    return y
+
+
+# ------------------------------------------------------------------------------------------ goldens
+def toy_arrays(fmt):
+    T = O.TOY
+    if fmt == "csr":
+        return dict(off=dev(T["csr_off"]), col=dev(T["csr_col"]), val=dev(T["val"]))
+    if fmt == "coo":
+        return dict(row=dev(T["coo_row"]), col=dev(T["csr_col"]), val=dev(T["val"]))
+    return dict(off=dev(T["sell_off"]), col=dev(T["sell_col"]), val=dev(T["sell_val"]), slice_size=2, nnz=9)
+
+
+@pytest.mark.parametrize("fmt", ["csr", "coo", "sell"])
+@pytest.mark.parametrize("preprocess", [True, False])
+def test_toy_golden_exact(cs, b200, fmt, preprocess):
+    # spmv_csr_example.c:54,123-129 / spmv_coo_example.c:54 / spmv_sell_example.c:69 -- exact `!=` compare
+    y = run(cs, b200, fmt, 4, 4, toy_arrays(fmt), dev(O.TOY["x"]), torch.zeros(4, device="cuda"), 1.0, 0.0,
+            preprocess=preprocess)
+    assert np.array_equal(y.cpu().numpy(), O.TOY["y_result"])
+
+
+def test_spmvop_alpha_beta_golden(cs, b200):
+    # spmv_csr_op_example.c:169-173,288-289,307-326: fp64, alpha 1, beta 3, tol 1e-14
+    T = O.TOY
+    arrays = dict(off=dev(T["csr_off"]), col=dev(T["csr_col"]), val=dev(T["val"].astype(np.float64)))
+    y = run(cs, b200, "csr", 4, 4, arrays, dev(T["x"].astype(np.float64)), dev(np.array([5.0, 6, 7, 8])), 1.0, 3.0)
+    assert np.max(np.abs(y.cpu().numpy() - np.array([34.0, 26, 72, 76]))) <= 1e-14
+
+
+@pytest.mark.parametrize("name", ["spmv_csr", "spmv_coo", "spmv_sell"])
+def test_reference_sample_passes_through_the_shim(name):
+    """The unmodified reference sample, linked -lb200spmv -lcusparse (oracle/Makefile), must print PASSED."""
+    exe = os.path.join(ROOT, "oracle", "_ref", f"{name}_example.b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, B200SPMV_LOG="1"))
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert f"{name}_example test PASSED" in p.stdout
+    assert "[b200spmv] SpMV" in p.stderr and "forwarded" not in p.stderr   # our kernel ran, not the closed one
+
+
+def _trace(out):
+    return [l for l in out.splitlines() if "rror" in l or "teration" in l]
+
+
+@pytest.mark.parametrize("name,iters", [("cg", 39), ("bicgstab", 13)])
+def test_solver_samples_reproduce_the_readme_trace(name, iters):
+    """cuSPARSE/cg/README.md:78-99 (39 iterations, final 4.39e-07) and bicgstab/README.md:77-93 (13 iterations):
+    the samples only print; the shim-linked binary must converge like the closed library does."""
+    ours = os.path.join(ROOT, "oracle", "_ref", f"{name}_example.b200")
+    theirs = os.path.join(ROOT, "oracle", "_ref", f"{name}_example.cusparse")
+    if not os.path.exists(ours):
+        pytest.skip("oracle/_ref not built")
+    a = subprocess.run([ours], capture_output=True, text=True, timeout=300)
+    b = subprocess.run([theirs], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0, a.stdout[-2000:] + a.stderr[-2000:]
+    assert b.returncode == 0
+    ta, tb = _trace(a.stdout), _trace(b.stdout)
+    na = sum("teration =" in l or "=== ITERATION" in l.upper() for l in ta)
+    nb = sum("teration =" in l or "=== ITERATION" in l.upper() for l in tb)
+    assert na == nb, (ta[-3:], tb[-3:])
+    # final residual lines agree to the printed precision's leading digits
+    fa = [l for l in a.stdout.splitlines() if "Final error norm" in l]
+    fb = [l for l in b.stdout.splitlines() if "Final error norm" in l]
+    assert fa and fb
+    va, vb = float(fa[0].split("=")[-1]), float(fb[0].split("=")[-1])
+    assert abs(va - vb) <= 1e-2 * abs(vb) + 1e-12, (fa, fb)
+
+
+# ---------------------------------------------------------------------------- oracle + closed library
+def rmat_case(rows, avg, dtype, seed):
+    off, col, val = O.rmat_csr(rows, avg_nnz=avg, seed=seed, val_seed=seed + 1, dtype=NP[dtype])
+    x = O.uniform(seed + 2, rows, NP[dtype])
+    y0 = O.uniform(seed + 3, rows, NP[dtype])
+    return off, col, val, x, y0
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (-1.0, 1.0), (0.75, 0.0), (2.5, -0.5)])
+def test_csr_rmat_vs_oracle_and_cusparse(cs, b200, closed, dtype, alpha, beta):
+    rows = 60000
+    off, col, val, x, y0 = rmat_case(rows, 16, dtype, 21)
+    assert np.diff(off).max() >= 2048, "case must contain rows that get split between tiles"
+    want = O.spmv_csr(off, col, val, x, y0, alpha, beta)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    got = run(cs, b200, "csr", rows, rows, arrays, dev(x), dev(y0), alpha, beta)
+    lib = run(cs, closed, "csr", rows, rows, arrays, dev(x), dev(y0), alpha, beta)
+    assert relerr(got.cpu().numpy(), want) < TOL[dtype]
+    assert relerr(got.cpu().numpy(), lib.cpu().numpy()) < TOL[dtype]
+    # bit-reproducible: same plan, same summation order
+    again = run(cs, b200, "csr", rows, rows, arrays, dev(x), dev(y0), alpha, beta)
+    assert torch.equal(got, again)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_csr_without_preprocess_and_buffer_reuse(cs, b200, dtype):
+    """cg_example.c:409-418 -> 156-160,220-224: no _preprocess call, one buffer, different x / y / alpha / beta."""
+    rows = 30000
+    off, col, val, x, y0 = rmat_case(rows, 8, dtype, 31)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    op = cs.SpMVOperator(b200, "csr", rows, rows, arrays, preprocess=False)
+    for (alpha, beta, sx) in [(0.75, 0.0, 1), (-1.0, 1.0, 2), (1.0, 0.0, 3)]:
+        xs = O.uniform(100 + sx, rows, NP[dtype])
+        y = dev(y0)
+        op(dev(xs), y, alpha, beta)
+        torch.cuda.synchronize()
+        assert relerr(y.cpu().numpy(), O.spmv_csr(off, col, val, xs, y0, alpha, beta)) < TOL[dtype]
+    op.close()
+
+
+def test_csr_in_place_residual_update(cs, b200):
+    # cg_example.c:153-160: R = B; R = -A*X + R with y aliased in/out
+    off, col, val = O.gen_stencil5(150)
+    n = 150 * 150
+    x = O.uniform(5, n)
+    b = O.spmv_csr(off, col, val, np.ones(n), alpha=0.75)
+    want = O.spmv_csr(off, col, val, x, b, -1.0, 1.0)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    got = run(cs, b200, "csr", n, n, arrays, dev(x), dev(b), -1.0, 1.0, preprocess=False)
+    assert relerr(got.cpu().numpy(), want) < 1e-13
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_csr_base_one(cs, b200, closed, dtype):
+    # cuSOLVERSp2cuDSS/csreigvsi2cuDSS_double.cpp:139-141,319 creates base-1 CSR descriptors
+    rows = 20000
+    off, col, val, x, y0 = rmat_case(rows, 12, dtype, 41)
+    arrays = dict(off=dev(off + 1), col=dev(col + 1), val=dev(val))
+    want = O.spmv_csr(off, col, val, x, y0, 1.5, 0.25)
+    got = run(cs, b200, "csr", rows, rows, arrays, dev(x), dev(y0), 1.5, 0.25, base=1)
+    lib = run(cs, closed, "csr", rows, rows, arrays, dev(x), dev(y0), 1.5, 0.25, base=1)
+    assert relerr(got.cpu().numpy(), want) < TOL[dtype]
+    assert relerr(got.cpu().numpy(), lib.cpu().numpy()) < TOL[dtype]
+
+
+def lens_to_csr(lens, cols, seed, dtype=np.float64):
+    rng = np.random.default_rng(seed)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    col = np.concatenate([np.sort(rng.choice(cols, size=l, replace=False)) for l in lens] + [np.zeros(0, int)]).astype(np.int32)
+    val = rng.uniform(-1, 1, off[-1]).astype(dtype)
+    return off, col, val
+
+
+EDGE = {
+    "all_empty": np.zeros(5000, int),
+    "single_huge_row": np.array([100000]),
+    "huge_then_tiny": np.concatenate([[50000], np.ones(3000, int), [0] * 500, [700], [511], [512], [513]]),
+    "exactly_long": np.full(100, 512),
+    "just_below_long": np.full(100, 511),
+    "tile_sized_rows": np.full(20, 2048),
+    "alternating": np.tile([0, 1, 4095, 0, 0, 3], 50),
+    "one_by_one": np.array([1]),
+    "trailing_empty": np.concatenate([np.full(10, 40), np.zeros(9000, int)]),
+    "leading_empty": np.concatenate([np.zeros(9000, int), np.full(10, 40)]),
+}
+
+
+@pytest.mark.parametrize("name", list(EDGE))
+def test_csr_edge_profiles(cs, b200, closed, name):
+    lens = EDGE[name]
+    rows, cols = lens.size, 120000
+    off, col, val = lens_to_csr(lens, cols, 3)
+    x = O.uniform(1, cols)
+    y0 = O.uniform(2, rows)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    for alpha, beta in [(1.0, 0.0), (-2.0, 0.5)]:
+        want = O.spmv_csr(off, col, val, x, y0, alpha, beta)
+        got = run(cs, b200, "csr", rows, cols, arrays, dev(x), dev(y0), alpha, beta).cpu().numpy()
+        assert relerr(got, want) < 1e-12, (name, alpha, beta)
+        if off[-1] > 0:
+            lib = run(cs, closed, "csr", rows, cols, arrays, dev(x), dev(y0), alpha, beta).cpu().numpy()
+            assert relerr(got, lib) < 1e-12
+
+
+def test_beta_zero_does_not_read_y(cs, b200):
+    # spmv_csr_example.c:61-78 copies hY = 0 but a caller may pass uninitialised / NaN y with beta = 0
+    off, col, val = O.gen_stencil5(64)
+    n = 64 * 64
+    x = O.uniform(8, n)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    y0 = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    got = run(cs, b200, "csr", n, n, arrays, dev(x), y0, 1.0, 0.0)
+    assert relerr(got.cpu().numpy(), O.spmv_csr(off, col, val, x)) < 1e-13
+
+
+def test_device_pointer_mode(cs, b200):
+    # cusparse.h:275-278: alpha / beta may live in device memory
+    rows = 10000
+    off, col, val, x, y0 = rmat_case(rows, 10, torch.float64, 51)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    op = cs.SpMVOperator(b200, "csr", rows, rows, arrays)
+    b200.cusparseSetPointerMode(op.handle, cs.CUSPARSE_POINTER_MODE_DEVICE)
+    y = dev(y0)
+    op(dev(x), y, dev(np.array([-0.5])), dev(np.array([2.0])))
+    torch.cuda.synchronize()
+    b200.cusparseSetPointerMode(op.handle, cs.CUSPARSE_POINTER_MODE_HOST)
+    op.close()
+    assert relerr(y.cpu().numpy(), O.spmv_csr(off, col, val, x, y0, -0.5, 2.0)) < 1e-12
+
+
+def test_non_default_stream_and_graph_capture(cs, b200):
+    """cuSPARSE/graph_capture/graph_capture_example.c:118-135 pattern: the call must be capturable (no sync / alloc)."""
+    rows = 20000
+    off, col, val, x, y0 = rmat_case(rows, 16, torch.float64, 61)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    xs, y = dev(x), dev(y0)
+    want = O.spmv_csr(off, col, val, x, y0, 1.0, 0.0)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        op = cs.SpMVOperator(b200, "csr", rows, rows, arrays)   # handle bound to stream s
+        op(xs, y, 1.0, 0.0)                                     # warm-up outside capture
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        y.zero_()
+        with torch.cuda.graph(g, stream=s):
+            op(xs, y, 1.0, 0.0)
+        y.zero_()
+        g.replay()
+        g.replay()
+    torch.cuda.synchronize()
+    assert relerr(y.cpu().numpy(), want) < 1e-12
+    op.close()
+
+
+def test_unsupported_combinations_are_forwarded_not_broken(cs, b200, closed):
+    """64-bit indices are outside our kernels: the shim must hand the call to the closed library unchanged."""
+    rows = 5000
+    off, col, val, x, y0 = rmat_case(rows, 8, torch.float64, 71)
+    arrays = dict(off=dev(off.astype(np.int64)), col=dev(col.astype(np.int64)), val=dev(val))
+    got = run(cs, b200, "csr", rows, rows, arrays, dev(x), dev(y0), 1.0, 0.0)
+    assert relerr(got.cpu().numpy(), O.spmv_csr(off, col, val, x)) < 1e-12
+
+
+def test_shape_mismatch_is_an_error(cs, b200):
+    T = O.TOY
+    h = b200.cusparseCreate()
+    m = b200.cusparseCreateCsr(4, 4, 9, dev(T["csr_off"]), dev(T["csr_col"]), dev(T["val"]))
+    xv = torch.zeros(3, device="cuda")
+    yv = torch.zeros(4, device="cuda")
+    vx, vy = b200.cusparseCreateDnVec(3, xv), b200.cusparseCreateDnVec(4, yv)
+    buf = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    with pytest.raises(cs.CuSparseError):
+        b200.cusparseSpMV(h, cs.CUSPARSE_OPERATION_NON_TRANSPOSE, 1.0, m, vx, 0.0, vy, cs.CUDA_R_32F, 0, buf)
+    b200.cusparseDestroySpMat(m); b200.cusparseDestroyDnVec(vx); b200.cusparseDestroyDnVec(vy); b200.cusparseDestroy(h)
+
+
+# ------------------------------------------------------------------------------------------ COO / SELL
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (-1.0, 1.0)])
+def test_coo_vs_oracle_and_cusparse(cs, b200, closed, dtype, alpha, beta):
+    rows = 40000
+    off, col, val, x, y0 = rmat_case(rows, 16, dtype, 81)
+    row = O.csr_to_coo_rows(off)
+    want = O.spmv_coo(rows, row, col, val, x, y0, alpha, beta)
+    arrays = dict(row=dev(row), col=dev(col), val=dev(val))
+    got = run(cs, b200, "coo", rows, rows, arrays, dev(x), dev(y0), alpha, beta).cpu().numpy()
+    lib = run(cs, closed, "coo", rows, rows, arrays, dev(x), dev(y0), alpha, beta).cpu().numpy()
+    assert relerr(got, want) < TOL[dtype]
+    assert relerr(got, lib) < TOL[dtype]
+
+
+def test_coo_unsorted_and_tiny(cs, b200):
+    rows = 3000
+    off, col, val, x, y0 = rmat_case(rows, 8, torch.float64, 91)
+    row = O.csr_to_coo_rows(off)
+    p = np.random.default_rng(0).permutation(row.size)
+    arrays = dict(row=dev(row[p]), col=dev(col[p]), val=dev(val[p]))
+    got = run(cs, b200, "coo", rows, rows, arrays, dev(x), dev(y0), 2.0, 0.5).cpu().numpy()
+    assert relerr(got, O.spmv_coo(rows, row, col, val, x, y0, 2.0, 0.5)) < 1e-12
+    # nnz = 0: y = beta*y
+    arrays = dict(row=torch.zeros(0, dtype=torch.int32, device="cuda"), col=torch.zeros(0, dtype=torch.int32, device="cuda"),
+                  val=torch.zeros(0, dtype=torch.float64, device="cuda"))
+    got = run(cs, b200, "coo", rows, rows, arrays, dev(x), dev(y0), 2.0, 0.5).cpu().numpy()
+    assert np.array_equal(got, 0.5 * y0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("slice_size", [32, 2, 7, 64])
+def test_sell_vs_oracle_and_cusparse(cs, b200, closed, dtype, slice_size):
+    # config 3's matrix family: 7-pt Laplacian (laplace_generator.hxx:34-107) in Sliced-ELL, padding col -1
+    nx = 24
+    off, col, val = O.gen_laplace7(nx)
+    val = val.astype(NP[dtype])
+    n = nx ** 3
+    so, sc, sv = O.csr_to_sell(off, col, val, slice_size)
+    x = O.uniform(3, n, NP[dtype])
+    y0 = O.uniform(4, n, NP[dtype])
+    arrays = dict(off=dev(so), col=dev(sc), val=dev(sv), slice_size=slice_size, nnz=int(col.size))
+    for alpha, beta in [(1.0, 0.0), (-1.0, 1.0)]:
+        want = O.spmv_sell(n, slice_size, so, sc, sv, x, y0, alpha, beta)
+        got = run(cs, b200, "sell", n, n, arrays, dev(x), dev(y0), alpha, beta).cpu().numpy()
+        lib = run(cs, closed, "sell", n, n, arrays, dev(x), dev(y0), alpha, beta).cpu().numpy()
+        assert relerr(got, want) < TOL[dtype]
+        assert relerr(got, lib) < TOL[dtype]
+
+
+def test_sell_ragged_rmat(cs, b200):
+    rows = 10000 + 13   # last slice is partial
+    off, col, val, x, y0 = rmat_case(rows, 6, torch.float64, 95)
+    so, sc, sv = O.csr_to_sell(off, col, val, 32)
+    arrays = dict(off=dev(so), col=dev(sc), val=dev(sv), slice_size=32, nnz=int(col.size))
+    got = run(cs, b200, "sell", rows, rows, arrays, dev(x), dev(y0), 1.0, 2.0).cpu().numpy()
+    assert relerr(got, O.spmv_csr(off, col, val, x, y0, 1.0, 2.0)) < 1e-12
+
+
+# ------------------------------------------------------------------ bit-exact integer work on the device
+def read_plan(buffer, num_tiles):
+    from cudalibrarysamples_b200 import lib
+    o = lib.shim().b200spmv_csr_plan_tiles_offset()
+    raw = buffer[o:o + (num_tiles + 1) * 8].view(torch.int32).view(-1, 2)
+    return raw.cpu().numpy()
+
+
+@pytest.mark.parametrize("case", ["rmat", "stencil", "huge_then_tiny", "empty"])
+@pytest.mark.parametrize("base", [0, 1])
+def test_partition_is_bit_exact(cs, b200, case, base):
+    from cudalibrarysamples_b200 import lib
+    L = lib.shim()
+    t, l, b = C.c_int32(), C.c_int32(), C.c_int32()
+    L.b200spmv_csr_plan_params(C.byref(t), C.byref(l), C.byref(b))
+    if case == "rmat":
+        off = O.rmat_csr(200000, avg_nnz=16, seed=5, val_seed=6)[0]
+    elif case == "stencil":
+        off = O.gen_stencil5(300)[0]
+    elif case == "empty":
+        off = np.zeros(30001, np.int32)
+    else:
+        off = np.concatenate([[0], np.cumsum(EDGE["huge_then_tiny"])]).astype(np.int32)
+    off = off + base
+    rows, nnz = off.size - 1, int(off[-1]) - base
+    nt = L.b200spmv_csr_num_tiles(C.c_int64(rows), C.c_int64(nnz))
+    ws = torch.zeros(L.b200spmv_csr_workspace_bytes(C.c_int64(rows), C.c_int64(nnz)), dtype=torch.uint8, device="cuda")
+    d_off = dev(off)
+    rc = L.b200spmv_csr_analyze(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_int64(rows), C.c_int64(nnz),
+                                C.c_void_p(d_off.data_ptr()), C.c_int32(base), C.c_void_p(ws.data_ptr()))
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = read_plan(ws, nt)
+    want = csr_partition(off, base, t.value, l.value)
+    assert np.array_equal(got, want)
+    assert check_partition(got, off, base, t.value, l.value)
+
+
+def test_device_generators_are_bit_identical_to_the_oracle():
+    from cudalibrarysamples_b200 import workloads as W
+    off, col, val = W.rmat_csr(30000, avg_nnz=16, seed=42, val_seed=43)
+    o2, c2, v2 = O.rmat_csr(30000, avg_nnz=16, seed=42, val_seed=43)
+    assert np.array_equal(off.cpu().numpy(), o2) and np.array_equal(col.cpu().numpy(), c2)
+    assert np.array_equal(val.cpu().numpy(), v2)
+    assert np.array_equal(W.uniform(44, 1000, torch.float32).cpu().numpy(), O.uniform(44, 1000, np.float32))
+    for a, b in zip(W.stencil5_csr(97), O.gen_stencil5(97)):
+        assert np.array_equal(a.cpu().numpy(), b)
+    for a, b in zip(W.stencil5_csr(31, 0.3, 0.3, 0.2), O.gen_stencil5(31, 0.3, 0.3, 0.2)):
+        assert np.array_equal(a.cpu().numpy(), b)
+    for a, b in zip(W.laplace7_csr(13), O.gen_laplace7(13)):
+        assert np.array_equal(a.cpu().numpy(), b)
+    off, col, val = O.gen_laplace7(9)
+    for ss in (32, 5):
+        for a, b in zip(W.csr_to_sell(dev(off), dev(col), dev(val), ss), O.csr_to_sell(off, col, val, ss)):
+            assert np.array_equal(a.cpu().numpy(), b)
+    assert np.array_equal(W.csr_to_coo_rows(dev(off)).cpu().numpy(), O.csr_to_coo_rows(off))

@@ -1,0 +1,92 @@
+"""CPU, world_size 2 (gloo): row-block sharding + the padded all-gather of x, local product by the CPU oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cudalibrarysamples_b200.sharded import ShardedCsr, split_rows_by_nnz
+from oracle import oracle as O
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_op(rows, cols, arrays):
+    off, col, val = (arrays[k].numpy() for k in ("off", "col", "val"))
+
+    def op(x, y, alpha, beta):
+        y.copy_(torch.from_numpy(O.spmv_csr(off, col, val, x.numpy(), y.numpy(), alpha, beta)))
+        return y
+    return op
+
+
+def _worker(rank, world, port, rows, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        off, col, val = (torch.from_numpy(a) for a in O.rmat_csr(rows, avg_nnz=8, seed=3, val_seed=4))
+        x = torch.from_numpy(O.uniform(5, rows))
+        y0 = torch.from_numpy(O.uniform(6, rows))
+        sh = ShardedCsr(off, col, val, rank, world, _oracle_op)
+        xs, ys = sh.new_shard(x), sh.new_shard(y0)
+        sh.spmv(xs, ys, alpha=-1.0, beta=1.0)
+        # second product chained on the first (CG style: y shard becomes the next x shard)
+        zs = sh.new_shard()
+        sh.spmv(ys, zs, alpha=1.0, beta=0.0)
+        # per-rank non-zero balance and the reassembled x
+        gathered = sh.unpad(sh.x_full)
+        out = [None] * world
+        dist.all_gather_object(out, dict(rank=rank, r0=sh.r0, r1=sh.r1, nnz=sh.nnz, y=ys[:sh.rows].numpy(),
+                                         z=zs[:sh.rows].numpy(), xg=gathered.numpy()))
+        if rank == 0:
+            q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_spmv_matches_single_process(world):
+    rows = 4000
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, rows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    off, col, val = O.rmat_csr(rows, avg_nnz=8, seed=3, val_seed=4)
+    x, y0 = O.uniform(5, rows), O.uniform(6, rows)
+    y = O.spmv_csr(off, col, val, x, y0, -1.0, 1.0)
+    z = O.spmv_csr(off, col, val, y)
+    out.sort(key=lambda d: d["rank"])
+    assert out[0]["r0"] == 0 and out[-1]["r1"] == rows
+    for a, b in zip(out[:-1], out[1:]):
+        assert a["r1"] == b["r0"]
+    got_y = np.concatenate([d["y"] for d in out])
+    got_z = np.concatenate([d["z"] for d in out])
+    assert np.array_equal(got_y, y)          # same oracle arithmetic per row -> bit-identical
+    assert np.array_equal(got_z, z)
+    assert np.array_equal(out[0]["xg"], y)   # the last gather carried the y shards
+    nnzs = [d["nnz"] for d in out]
+    assert sum(nnzs) == off[-1]
+    assert max(nnzs) - min(nnzs) <= np.diff(off).max() + 1   # balanced up to one row
+
+
+def test_split_rows_by_nnz_edge_cases():
+    off = torch.tensor([0, 0, 0, 10, 10, 10], dtype=torch.int32)
+    b = split_rows_by_nnz(off, 4).tolist()
+    assert b[0] == 0 and b[-1] == 5 and all(x <= y for x, y in zip(b[:-1], b[1:]))
+    off = torch.zeros(8, dtype=torch.int32)
+    b = split_rows_by_nnz(off, 3).tolist()
+    assert b[0] == 0 and b[-1] == 7
