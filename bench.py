@@ -342,7 +342,7 @@ def run_ours(args):
             rel = float((torch.linalg.norm(y - y2) / torch.linalg.norm(y2)).item())
             closed = {"value": round(total_bytes / (ms_c / args.steps * 1e-3) / 1e9, 3), "unit": UNIT,
                       "ms_per_step": round(ms_c / args.steps, 4), "frac_of_peak": round(total_bytes / (ms_c / args.steps * 1e-3) / 1e9 / peak, 4),
-                      "rel_diff_vs_ours": rel, "what": "libcusparse 12.5.10 cusparseSpMV (preprocessed), same buffers, same loop"}
+                      "rel_diff_vs_ours": rel, "what": "closed libcusparse.so.12 cusparseSpMV (the copy torch ships; preprocessed), same buffers, same loop"}
             cop.close()
         except Exception as e:  # pragma: no cover
             closed = {"error": repr(e)}

@@ -9,8 +9,21 @@ import os
 
 from . import build as _build
 
+def _bundled_with_torch() -> str:
+    """torch's own libcusparse.so.12 (nvidia-cusparse-cu12 wheel).  Inside a Python process that imported torch, the
+    toolkit's libcusparse 12.9 cannot be loaded (torch already mapped an older libnvJitLink.so.12), so the closed
+    library used for handles and as the GPU oracle is the one torch ships; the C sample binaries use the toolkit's."""
+    try:
+        import torch
+        p = os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "cusparse", "lib", "libcusparse.so.12")
+        return p if os.path.exists(p) else ""
+    except Exception:
+        return ""
+
+
 REAL_CUSPARSE_CANDIDATES = (
     os.environ.get("B200SPMV_CUSPARSE", ""),
+    _bundled_with_torch(),
     "/usr/local/cuda/lib64/libcusparse.so.12",
     "libcusparse.so.12",
 )
@@ -20,27 +33,28 @@ _real = None
 _real_path = None
 
 
-def real_cusparse_path() -> str:
-    global _real_path
-    if _real_path is None:
-        for p in REAL_CUSPARSE_CANDIDATES:
-            if not p:
-                continue
-            if "/" in p and not os.path.exists(p):
-                continue
-            _real_path = p
-            break
-        else:
-            raise RuntimeError("real libcusparse.so.12 not found (set B200SPMV_CUSPARSE)")
-    return _real_path
-
-
 def real() -> C.CDLL:
     """The closed libcusparse.so.12: cusparseCreate/Destroy/SetStream/SetPointerMode, and the GPU oracle."""
-    global _real
+    global _real, _real_path
     if _real is None:
-        _real = C.CDLL(real_cusparse_path(), mode=C.RTLD_LOCAL)
+        errors = []
+        for p in REAL_CUSPARSE_CANDIDATES:
+            if not p or ("/" in p and not os.path.exists(p)):
+                continue
+            try:
+                _real = C.CDLL(p, mode=C.RTLD_LOCAL)
+                _real_path = p
+                break
+            except OSError as e:
+                errors.append(f"{p}: {e}")
+        if _real is None:
+            raise RuntimeError("real libcusparse.so.12 could not be loaded (set B200SPMV_CUSPARSE): " + "; ".join(errors))
     return _real
+
+
+def real_cusparse_path() -> str:
+    real()
+    return _real_path
 
 
 def shim(build_if_missing: bool = False) -> C.CDLL:
