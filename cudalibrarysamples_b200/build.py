@@ -39,24 +39,29 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into cudalibrarysamples_b200/libb200spmv.so."""
-    if not force and not needs_build():
+def build_native(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str | None = None,
+                 tag: str = "") -> str:
+    """Compile every CUDA source for sm_100a into cudalibrarysamples_b200/libb200spmv.so.
+
+    extra_flags / out_path / tag build a tuning variant (scripts/sweep.py) next to the default library."""
+    variant = bool(extra_flags) or out_path is not None
+    if not variant and not force and not needs_build():
         return LIB_PATH
+    target = out_path or LIB_PATH
     objs = []
-    build_dir = os.path.join(PKG_DIR, "build")
+    build_dir = os.path.join(PKG_DIR, "build", tag) if tag else os.path.join(PKG_DIR, "build")
     os.makedirs(build_dir, exist_ok=True)
     log = []
     for s in SOURCES:
         o = os.path.join(build_dir, s + ".o")
-        cmd = [nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc(), *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, s), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:
             sys.stderr.write(log[-1])
             raise RuntimeError(f"nvcc failed on {s}")
         objs.append(o)
-    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs, "-ldl", "-lpthread"]
+    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", target, *objs, "-ldl", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
@@ -66,7 +71,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

@@ -10,9 +10,9 @@
 //     so ordinary rows never straddle tiles and need no carry/fix-up; only rows >= LONG_ROW are cut, and
 //     their per-tile partial sums are combined by the last-arriving tile (arrival counter, fixed
 //     summation order -> bit-reproducible, single launch, no spin-waits).
-//   * mv: one CTA per tile.  Phase 1 streams val[]/col_ind[] with 128-bit L1-bypassing loads
-//     (coalesced, all loads of the tile in flight before the first use), gathers x through L1/L2 and
-//     parks the products in shared memory.  Phase 2 reduces each row from shared memory with a group of
+//   * mv: one CTA per tile.  Phase 1 streams val[]/col_ind[] with L1-bypassing loads (every warp-level
+//     load is one aligned 128 B / 256 B segment, several steps in flight before the first use), gathers x
+//     through L1/L2 and parks the products in shared memory.  Phase 2 reduces each row from shared memory with a group of
 //     g = 1..32 lanes (g picked per tile from its mean row length) and a warp-shuffle tree, and writes y
 //     once.  No tensor cores: 0.125-0.17 flop/B, HBM-bound.
 #include "spmv_common.cuh"
@@ -20,12 +20,33 @@
 
 namespace b200 {
 
-constexpr int CSR_TILE_ITEMS = 2048;  // merge items (row ends + non-zeros) per tile
-constexpr int CSR_LONG_ROW   = 512;   // rows at least this long may be split between tiles
-constexpr int CSR_BLOCK      = 256;   // threads per CTA
+// Tunables (overridable with -D for the parameter sweeps in scripts/sweep.py)
+#ifndef B200_CSR_TILE_ITEMS
+#define B200_CSR_TILE_ITEMS 2048
+#endif
+#ifndef B200_CSR_LONG_ROW
+#define B200_CSR_LONG_ROW 512
+#endif
+#ifndef B200_CSR_BLOCK
+#define B200_CSR_BLOCK 256
+#endif
+#ifndef B200_CSR_BATCH
+#define B200_CSR_BATCH 4
+#endif
+#ifndef B200_CSR_MIN_CTAS
+#define B200_CSR_MIN_CTAS 1
+#endif
+#ifndef B200_CSR_ABLATE   // profiling only: 1 = skip phase 2, 2 = no x gather, 3 = neither (stream only)
+#define B200_CSR_ABLATE 0
+#endif
+constexpr int CSR_TILE_ITEMS = B200_CSR_TILE_ITEMS;  // merge items (row ends + non-zeros) per tile
+constexpr int CSR_LONG_ROW   = B200_CSR_LONG_ROW;    // rows at least this long may be split between tiles
+constexpr int CSR_BLOCK      = B200_CSR_BLOCK;       // threads per CTA
 constexpr int CSR_SMEM_ELEMS = CSR_TILE_ITEMS + CSR_LONG_ROW;  // max non-zeros a tile can hold
-constexpr int CSR_VEC        = 4;     // non-zeros per thread per load step (128-bit col load)
-constexpr int CSR_ITERS      = (CSR_SMEM_ELEMS + CSR_VEC - 1 + CSR_BLOCK * CSR_VEC - 1) / (CSR_BLOCK * CSR_VEC);
+constexpr int CSR_BATCH      = B200_CSR_BATCH;  // load steps whose loads are all issued before the first use
+// a tile's element range starts at a multiple of 32 (<= 31 masked lanes) and holds < CSR_SMEM_ELEMS non-zeros
+constexpr int CSR_STEPS      = (CSR_SMEM_ELEMS + 31 + CSR_BLOCK - 1) / CSR_BLOCK;
+constexpr int CSR_ITERS      = (CSR_STEPS + CSR_BATCH - 1) / CSR_BATCH * CSR_BATCH;
 
 constexpr size_t PLAN_HEADER_BYTES = 256;
 
@@ -97,7 +118,6 @@ struct CsrArgs {
     int        base;
     int        rows;
     int        nnz;
-    int        vec_ok;  // val/col 16-byte aligned -> 128-bit streaming loads
     Scalars<T> s;
     PlanView   plan;
 };
@@ -119,19 +139,20 @@ __device__ __forceinline__ T block_sum_range(const T* sP, int lo, int hi, T* sRe
     return tot;
 }
 
-// Rows [r_first, r_first + nrows) are complete inside the tile; products of non-zero j live at sP[j - ns].
+// Rows [r_first, r_first + nrows) are complete inside the tile; the products of row r live at
+// sP[sOff[r - rs] .. sOff[r - rs + 1]) (sOff = the tile's slice of rowOff, staged in phase 1, rebased to the tile).
 template <typename T, int G, int BLOCK>
-__device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, int r_first, int nrows, int ns,
-                                            T alpha, T beta) {
+__device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, const int* sOff, int rs, int r_first,
+                                            int nrows, T alpha, T beta) {
     constexpr int GROUPS = BLOCK / G;
     const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+    const int* so = sOff + (r_first - rs);
     for (int r0 = 0; r0 < nrows; r0 += GROUPS) {
         const int  ri = r0 + gid;
         const bool active = ri < nrows;
         T sum = T(0);
         if (active) {
-            const int r = r_first + ri;
-            const int s = __ldg(a.off + r) - a.base - ns, e = __ldg(a.off + r + 1) - a.base - ns;
+            const int s = so[ri], e = so[ri + 1];
             for (int k = s + gl; k < e; k += G) sum += sP[k];
         }
 #pragma unroll
@@ -165,9 +186,10 @@ __device__ __forceinline__ void split_row_arrive(const CsrArgs<T>& a, int R, T a
 }
 
 template <typename T>
-__global__ void __launch_bounds__(CSR_BLOCK) csr_tile_kernel(const CsrArgs<T> a) {
-    __shared__ T sP[CSR_SMEM_ELEMS];
-    __shared__ T sRed[CSR_BLOCK / 32];
+__global__ void __launch_bounds__(CSR_BLOCK, B200_CSR_MIN_CTAS) csr_tile_kernel(const CsrArgs<T> a) {
+    __shared__ T   sP[CSR_SMEM_ELEMS];
+    __shared__ int sOff[CSR_SMEM_ELEMS + 1];   // rowOff[rs .. re] - base - ns: a tile spans < CSR_SMEM_ELEMS rows
+    __shared__ T   sRed[CSR_BLOCK / 32];
 
     const int  b  = blockIdx.x;
     const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
@@ -175,43 +197,44 @@ __global__ void __launch_bounds__(CSR_BLOCK) csr_tile_kernel(const CsrArgs<T> a)
     const T alpha = a.s.a(), beta = a.s.b();
 
     // ---------------- phase 1: stream val/col, gather x, park products in shared memory -------------
+    // Lane l of a warp handles element (step*BLOCK + warp*32 + l): every load/gather instruction covers 32
+    // CONSECUTIVE non-zeros.  The streaming loads are then perfectly coalesced (the tile's first element is
+    // rounded down to a multiple of 32 so each warp-level load is one aligned 128 B / 256 B segment), the
+    // gathers of x see the sorted neighbouring columns of a row in one instruction (fewest L1TEX wavefronts:
+    // the gather rate of the SM, ~1 distinct 128 B line per clock, is what bounds this kernel on scattered
+    // matrices), and the shared-memory stores are bank-conflict free.
     {
-        const int al = ns & ~(CSR_VEC - 1);
-        const int nnz_vec_end = a.vec_ok ? (a.nnz & ~(CSR_VEC - 1)) : 0;  // below this, 4-wide loads are in bounds
-        int c[CSR_ITERS][CSR_VEC];
-        T   v[CSR_ITERS][CSR_VEC];
+        // the tile's slice of rowOff goes to shared memory first: its latency overlaps the val/col stream, and
+        // phase 2 then never waits on global memory
+        const int noff = (re < a.rows ? re : a.rows) - rs + 1;
+        for (int i = (int)threadIdx.x; i < noff; i += CSR_BLOCK) sOff[i] = __ldg(a.off + rs + i) - a.base - ns;
+        const int al   = ns & ~31;
+        const int lead = ns - al;                 // masked lanes in front of the tile
+        const int span = ne - al;                 // elements [lead, span) are live
+        const int* colp = a.col + al;
+        const T*   valp = a.val + al;
 #pragma unroll
-        for (int it = 0; it < CSR_ITERS; it++) {
-            const int i0 = al + (it * CSR_BLOCK + (int)threadIdx.x) * CSR_VEC;
-            if (i0 < ne) {
-                if (i0 + CSR_VEC <= nnz_vec_end) {
-                    const int4 cc = ldg_stream_int4(a.col + i0);
-                    c[it][0] = cc.x; c[it][1] = cc.y; c[it][2] = cc.z; c[it][3] = cc.w;
-                    load4_stream(a.val + i0, v[it]);
-                } else {
+        for (int batch = 0; batch < CSR_ITERS; batch += CSR_BATCH) {
+            if (batch * CSR_BLOCK < span) {       // block-uniform
+                int c[CSR_BATCH];
+                T   v[CSR_BATCH], xv[CSR_BATCH];
 #pragma unroll
-                    for (int j = 0; j < CSR_VEC; j++) {
-                        const bool ok = i0 + j < a.nnz;
-                        c[it][j] = ok ? ldg_stream(a.col + i0 + j) : a.base;
-                        v[it][j] = ok ? ldg_stream(a.val + i0 + j) : T(0);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < CSR_ITERS; it++) {
-            const int i0 = al + (it * CSR_BLOCK + (int)threadIdx.x) * CSR_VEC;
-            if (i0 < ne) {
-                T xv[CSR_VEC];
-#pragma unroll
-                for (int j = 0; j < CSR_VEC; j++) {
-                    const int i = i0 + j;
-                    xv[j] = (i >= ns && i < ne) ? __ldg(a.x + (c[it][j] - a.base)) : T(0);
+                for (int k = 0; k < CSR_BATCH; k++) {
+                    const int e = (batch + k) * CSR_BLOCK + (int)threadIdx.x;
+                    const bool live = e >= lead && e < span;
+                    c[k] = live ? ldg_stream(colp + e) : a.base;
+                    v[k] = live ? ldg_stream(valp + e) : T(0);
                 }
 #pragma unroll
-                for (int j = 0; j < CSR_VEC; j++) {
-                    const int i = i0 + j;
-                    if (i >= ns && i < ne) sP[i - ns] = v[it][j] * xv[j];
+                for (int k = 0; k < CSR_BATCH; k++) {
+                    const int e = (batch + k) * CSR_BLOCK + (int)threadIdx.x;
+                    const bool live = e >= lead && e < span;
+                    xv[k] = (live && !(B200_CSR_ABLATE & 2)) ? __ldg(a.x + (c[k] - a.base)) : T(c[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < CSR_BATCH; k++) {
+                    const int e = (batch + k) * CSR_BLOCK + (int)threadIdx.x;
+                    if (e >= lead && e < span) sP[e - lead] = v[k] * xv[k];
                 }
             }
         }
@@ -219,35 +242,33 @@ __global__ void __launch_bounds__(CSR_BLOCK) csr_tile_kernel(const CsrArgs<T> a)
     __syncthreads();
 
     // ---------------- phase 2: per-row reduction out of shared memory ------------------------------
+    if (B200_CSR_ABLATE & 1) { if (sP[threadIdx.x] == T(1.2345)) a.y[0] = sP[0]; return; }
     const int cnt = ne - ns;
     bool head = false;
     int  head_end = 0;  // products [0, head_end) belong to the split row rs
-    if (rs < a.rows) {
-        const int o0 = __ldg(a.off + rs) - a.base;
-        if (ns > o0) {
-            head = true;
-            const int o1 = __ldg(a.off + rs + 1) - a.base;
-            head_end = (o1 < ne ? o1 : ne) - ns;
-        }
+    if (rs < a.rows && sOff[0] < 0) {            // the tile starts inside row rs
+        head = true;
+        const int o1 = re > rs ? sOff[1] : cnt;  // re == rs: the whole tile lies inside row rs
+        head_end = o1 < cnt ? o1 : cnt;
     }
     const int r_first = rs + (head ? 1 : 0);
     const int nrows   = re - r_first;  // complete rows (may be <= 0)
     int  tail_beg = cnt;               // products [tail_beg, cnt) belong to the split row re
     bool tail = false;
     if (re < a.rows && re >= r_first) {
-        const int o0 = __ldg(a.off + re) - a.base;
-        if (ne > o0) { tail = true; tail_beg = o0 - ns; }
+        const int o0 = sOff[re - rs];
+        if (cnt > o0) { tail = true; tail_beg = o0; }
     }
 
     if (nrows > 0) {
         const int body = tail_beg - head_end;
         const int avg2 = body / (2 * nrows);  // half the mean row length
-        if      (avg2 <= 1)  reduce_rows<T, 1,  CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
-        else if (avg2 <= 2)  reduce_rows<T, 2,  CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
-        else if (avg2 <= 4)  reduce_rows<T, 4,  CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
-        else if (avg2 <= 8)  reduce_rows<T, 8,  CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
-        else if (avg2 <= 16) reduce_rows<T, 16, CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
-        else                 reduce_rows<T, 32, CSR_BLOCK>(a, sP, r_first, nrows, ns, alpha, beta);
+        if      (avg2 <= 1)  reduce_rows<T, 1,  CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
+        else if (avg2 <= 2)  reduce_rows<T, 2,  CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
+        else if (avg2 <= 4)  reduce_rows<T, 4,  CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
+        else if (avg2 <= 8)  reduce_rows<T, 8,  CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
+        else if (avg2 <= 16) reduce_rows<T, 16, CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
+        else                 reduce_rows<T, 32, CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
     }
 
     if (head) {  // block-uniform
@@ -275,7 +296,6 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
     CsrArgs<T> a;
     a.off = (const int*)off; a.col = (const int*)col; a.val = (const T*)val;
     a.x = (const T*)x; a.y = (T*)y; a.base = base; a.rows = (int)rows; a.nnz = (int)nnz;
-    a.vec_ok = (((uintptr_t)col | (uintptr_t)val) & 15) == 0;
     if (on_device) { a.s.alpha = T(0); a.s.beta = T(0); a.s.alpha_dev = (const T*)alpha; a.s.beta_dev = (const T*)beta; }
     else { a.s.alpha = *(const T*)alpha; a.s.beta = *(const T*)beta; a.s.alpha_dev = nullptr; a.s.beta_dev = nullptr; }
     plan_layout(nt, ws, &a.plan);

@@ -63,12 +63,18 @@ def _ptr(t):
 class Api:
     """One instance per implementation under test."""
 
-    def __init__(self, impl: str = "b200"):
+    def __init__(self, impl: str = "b200", lib_path: str | None = None):
         if impl not in ("b200", "cusparse"):
             raise ValueError(impl)
         self.impl = impl
         self.real = _lib.real()
-        self.lib = _lib.shim() if impl == "b200" else self.real
+        if impl == "cusparse":
+            self.lib = self.real
+        elif lib_path is None:
+            self.lib = _lib.shim()
+        else:   # a tuning variant of the product library (scripts/sweep.py); same ABI
+            _lib.shim()
+            self.lib = C.CDLL(lib_path, mode=C.RTLD_LOCAL)
 
     # ---- helpers ---------------------------------------------------------------------------------
     def _call(self, lib, name, *args):

@@ -63,7 +63,7 @@ def shim(build_if_missing: bool = False) -> C.CDLL:
     if _shim is None:
         # the shim must dlopen the very same libcusparse instance that creates the handles we pass to it
         os.environ["B200SPMV_CUSPARSE"] = real_cusparse_path()
-        path = _build.LIB_PATH
+        path = os.environ.get("B200SPMV_LIB") or _build.LIB_PATH   # B200SPMV_LIB: a tuning variant (scripts/sweep.py)
         if not os.path.exists(path):
             if build_if_missing:
                 _build.build_native()

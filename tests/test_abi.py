@@ -55,7 +55,8 @@ def test_sass_is_sm100a_and_streams_with_128bit_loads(built_lib):
     m = re.search(r"Function : \S*csr_tile_kernelId.*?(?=Function :|\Z)", sass, re.S)
     assert m, "fp64 CSR tile kernel not found in the cubin"
     body = m.group(0)
-    assert re.search(r"LDG\.E\.NA\.128", body)   # 128-bit, L1 no-allocate streaming loads of val[] / col_ind[]
+    assert re.search(r"LDG\.E\.NA\.64", body)    # L1 no-allocate streaming loads of val[] (coalesced: 256 B per warp)
+    assert re.search(r"LDG\.E\.64\.CONSTANT", body)   # x gathered through the read-only L1 path
     assert "SHFL" in body                 # warp-shuffle row reduction
     assert "HMMA" not in body and "UTC" not in body   # no tensor cores: HBM-bound gather-reduce
 
