@@ -37,6 +37,21 @@ if os.environ.get("SWEEP_SET") == "occ":
     VARIANTS = {f"t2048_b256_k{k}_occ{o}": dict(TILE=2048, LONG=512, BLOCK=256, BATCH=k, MIN=o) for k in (4, 8) for o in (4, 5, 6, 7)}
     VARIANTS.update({f"t1024_b128_k{k}_occ{o}": dict(TILE=1024, LONG=256, BLOCK=128, BATCH=k, MIN=o) for k in (4, 8) for o in (8, 12)})
     VARIANTS.update({f"t1024_b256_k4_occ{o}": dict(TILE=1024, LONG=256, BLOCK=256, BATCH=4, MIN=o) for o in (6, 8)})
+if os.environ.get("SWEEP_SET") == "pipe":
+    VARIANTS = {f"pipe_t2048_b256_o{po}_occ{o}": dict(TILE=2048, LONG=512, BLOCK=256, BATCH=4, MIN=o, KERNEL=1, OFFS=po)
+                for po in (2, 4) for o in (3, 4, 5, 6)}
+    VARIANTS.update({f"pipe_t1024_b128_o{po}_occ{o}": dict(TILE=1024, LONG=256, BLOCK=128, BATCH=4, MIN=o, KERNEL=1, OFFS=po)
+                     for po in (4,) for o in (6, 8, 10, 12)})
+    VARIANTS.update({f"pipe_t1024_b256_o2_occ{o}": dict(TILE=1024, LONG=256, BLOCK=256, BATCH=4, MIN=o, KERNEL=1, OFFS=2)
+                     for o in (4, 6, 8)})
+    VARIANTS.update({f"tile_t1024_b128_k8_occ12": dict(TILE=1024, LONG=256, BLOCK=128, BATCH=8, MIN=12, KERNEL=0)})
+if os.environ.get("SWEEP_SET") == "red":
+    VARIANTS = {}
+    for rr, ru in ((4, 2), (2, 4), (4, 1), (2, 2)):
+        for o in (3, 4, 5):
+            VARIANTS[f"pipe_r{rr}u{ru}_occ{o}"] = dict(TILE=2048, LONG=512, BLOCK=256, BATCH=4, MIN=o, KERNEL=1, OFFS=4, RR=rr, RU=ru)
+        VARIANTS[f"tile_r{rr}u{ru}_occ5"] = dict(TILE=2048, LONG=512, BLOCK=256, BATCH=4, MIN=5, KERNEL=0, RR=rr, RU=ru)
+        VARIANTS[f"pipe1024_r{rr}u{ru}_occ8"] = dict(TILE=1024, LONG=256, BLOCK=128, BATCH=4, MIN=8, KERNEL=1, OFFS=4, RR=rr, RU=ru)
 if os.environ.get("SWEEP_SET") == "ablate":
     VARIANTS = dict(ABL, t2048_b256_k4_occ6=VARIANTS["t2048_b256_k4_occ6"])
 
@@ -44,6 +59,11 @@ if os.environ.get("SWEEP_SET") == "ablate":
 def flags(v):
     if "ABL" in v:
         return flags({k: x for k, x in v.items() if k != "ABL"}) + [f"-DB200_CSR_ABLATE={v['ABL']}"]
+    if "RR" in v:
+        return flags({k: x for k, x in v.items() if k not in ("RR", "RU")}) + [f"-DB200_CSR_RED_ROWS={v['RR']}", f"-DB200_CSR_RED_U={v['RU']}"]
+    if "KERNEL" in v:
+        extra = [f"-DB200_CSR_KERNEL={v['KERNEL']}"] + ([f"-DB200_CSR_PIPE_OFFS={v['OFFS']}"] if "OFFS" in v else [])
+        return flags({k: x for k, x in v.items() if k not in ("KERNEL", "OFFS")}) + extra
     return [f"-DB200_CSR_TILE_ITEMS={v['TILE']}", f"-DB200_CSR_LONG_ROW={v['LONG']}", f"-DB200_CSR_BLOCK={v['BLOCK']}",
             f"-DB200_CSR_BATCH={v['BATCH']}", f"-DB200_CSR_MIN_CTAS={v['MIN']}"]
 
@@ -55,7 +75,7 @@ def build():
         out = os.path.join(VDIR, f"libb200spmv_{tag}.so")
         b.build_native(extra_flags=flags(v), out_path=out, tag="v_" + tag)
         log = open(os.path.join(ROOT, "cudalibrarysamples_b200", "build", "v_" + tag, "build.log")).read()
-        i = log.find("csr_tile_kernelIdEE")
+        i = max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
         regs = log[i:i + 400].split("Used ")[1].split(",")[0] if i >= 0 else "?"
         print(tag, regs)
 

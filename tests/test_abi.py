@@ -52,8 +52,8 @@ def test_library_loads_without_a_gpu(built_lib):
 def test_sass_is_sm100a_and_streams_with_128bit_loads(built_lib):
     sass = subprocess.check_output(["cuobjdump", "-sass", built_lib], text=True)
     assert "sm_100a" in sass or "SM100" in sass.upper()
-    m = re.search(r"Function : \S*csr_tile_kernelId.*?(?=Function :|\Z)", sass, re.S)
-    assert m, "fp64 CSR tile kernel not found in the cubin"
+    m = re.search(r"Function : \S*csr_pipe_kernelId.*?(?=Function :|\Z)", sass, re.S)
+    assert m, "fp64 CSR kernel not found in the cubin"
     body = m.group(0)
     assert re.search(r"LDG\.E\.NA\.64", body)    # L1 no-allocate streaming loads of val[] (coalesced: 256 B per warp)
     assert re.search(r"LDG\.E\.64\.CONSTANT", body)   # x gathered through the read-only L1 path
