@@ -17,6 +17,8 @@
 //     once.  No tensor cores: 0.125-0.17 flop/B, HBM-bound.
 #include "spmv_common.cuh"
 #include "../../include/b200spmv.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace b200 {
 
@@ -33,11 +35,17 @@ namespace b200 {
 #ifndef B200_CSR_BATCH
 #define B200_CSR_BATCH 4
 #endif
-#ifndef B200_CSR_MIN_CTAS
-#define B200_CSR_MIN_CTAS 4
+#ifndef B200_CSR_MIN_CTAS        // -D override for sweeps: resident CTAs per SM the register allocator must allow
+#define B200_TILE_MIN_CTAS 5     // one-CTA-per-tile kernel: 48 registers
+#define B200_PIPE_MIN_CTAS 3     // persistent pipelined kernel: 80 registers (next tile's stream lives in registers)
+#define B200_RW_MIN_CTAS 4
+#else
+#define B200_TILE_MIN_CTAS B200_CSR_MIN_CTAS
+#define B200_PIPE_MIN_CTAS B200_CSR_MIN_CTAS
+#define B200_RW_MIN_CTAS B200_CSR_MIN_CTAS
 #endif
-#ifndef B200_CSR_KERNEL      // 0 = one CTA per tile, 1 = persistent software-pipelined CTAs
-#define B200_CSR_KERNEL 1
+#ifndef B200_CSR_KERNEL      // -D override for sweeps: -1 = runtime choice (default), 0 = one CTA per tile,
+#define B200_CSR_KERNEL -1   //  1 = persistent software-pipelined CTAs, 2 = warp-specialised TMA-fed, 3 = row-wise
 #endif
 #ifndef B200_CSR_PIPE_STEPS
 #define B200_CSR_PIPE_STEPS ((B200_CSR_TILE_ITEMS + B200_CSR_BLOCK - 1) / B200_CSR_BLOCK)
@@ -46,7 +54,7 @@ namespace b200 {
 #define B200_CSR_PIPE_OFFS 4
 #endif
 #ifndef B200_CSR_RED_ROWS     // rows a lane group reduces concurrently in phase 2
-#define B200_CSR_RED_ROWS 4
+#define B200_CSR_RED_ROWS 2
 #endif
 #ifndef B200_CSR_RED_U        // predicated product loads per lane and row before the fall-back loop
 #define B200_CSR_RED_U 2
@@ -160,17 +168,25 @@ struct CsrArgs {
     long long* trace;
 };
 
-// Sum sP[lo, hi) with the whole CTA, fixed order (bit-reproducible). Result valid on thread 0.
-template <typename T, int BLOCK>
-__device__ __forceinline__ T block_sum_range(const T* sP, int lo, int hi, T* sRed) {
+// The phase-2 code runs either on a whole CTA (tile / pipe kernels: __syncthreads) or on the "reduce" warps of a
+// warp-specialised CTA (named barrier BAR_ID over BLOCK threads); `tid` is the thread's index inside that group.
+template <int BLOCK, int BAR_ID>
+__device__ __forceinline__ void group_sync() {
+    if (BAR_ID == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR_ID), "n"(BLOCK) : "memory");
+}
+
+// Sum sP[lo, hi) with the whole group, fixed order (bit-reproducible). Result valid on group thread 0.
+template <typename T, int BLOCK, int BAR_ID>
+__device__ __forceinline__ T block_sum_range(const T* sP, int lo, int hi, T* sRed, int tid) {
     T s = T(0);
-    for (int k = lo + (int)threadIdx.x; k < hi; k += BLOCK) s += sP[k];
+    for (int k = lo + tid; k < hi; k += BLOCK) s += sP[k];
     s = warp_sum(s);
-    __syncthreads();  // sRed reuse
-    if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5] = s;
-    __syncthreads();
+    group_sync<BLOCK, BAR_ID>();  // sRed reuse
+    if ((tid & 31) == 0) sRed[tid >> 5] = s;
+    group_sync<BLOCK, BAR_ID>();
     T tot = T(0);
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
 #pragma unroll
         for (int w = 0; w < BLOCK / 32; w++) tot += sRed[w];
     }
@@ -181,26 +197,26 @@ __device__ __forceinline__ T block_sum_range(const T* sP, int lo, int hi, T* sRe
 // sP[sOff[r - rs] .. sOff[r - rs + 1]) (sOff = the tile's slice of rowOff, staged in phase 1, rebased to the tile).
 //
 // Every shared-memory access and every shuffle of this phase queues in the SM's single L1TEX FIFO behind the x
-// gathers of the other resident CTAs, so what matters is the NUMBER OF DEPENDENT STEPS, not the instruction count:
-// a group of G lanes therefore works on RED_ROWS rows at once -- all row bounds first, then all products (RED_U
-// predicated loads per lane and row, enough for rows up to RED_U*G long), then RED_ROWS interleaved shuffle trees.
+// gathers of the other resident warps, so what matters is the NUMBER OF DEPENDENT STEPS, not the instruction count:
+// a group of G lanes therefore works on ROWS rows at once -- all row bounds first, then all products (U predicated
+// loads per lane and row, enough for rows up to U*G long), then ROWS interleaved shuffle trees.
 constexpr int RED_ROWS = B200_CSR_RED_ROWS;
 constexpr int RED_U    = B200_CSR_RED_U;
 
-template <typename T, int G, int ROWS, int U, int BLOCK>
-__device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, const int* sOff, int rs, int r_first,
-                                            int nrows, T alpha, T beta) {
+template <typename T, typename OT, int G, int ROWS, int U, int BLOCK>
+__device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, const OT* sOff, int shift, int rs,
+                                            int r_first, int nrows, T alpha, T beta, int tid) {
     constexpr int GROUPS = BLOCK / G;
-    const int gid = threadIdx.x / G, gl = threadIdx.x % G;
-    const int* so = sOff + (r_first - rs);
+    const int gid = tid / G, gl = tid % G;
+    const OT* so = sOff + (r_first - rs);
     for (int r0 = 0; r0 < nrows; r0 += GROUPS * ROWS) {
         int k0[ROWS], e[ROWS];
 #pragma unroll
         for (int i = 0; i < ROWS; i++) {
             const int ri = r0 + i * GROUPS + gid;
             const bool active = ri < nrows;
-            k0[i] = (active ? so[ri] : 0) + gl;
-            e[i]  = active ? so[ri + 1] : 0;
+            k0[i] = (active ? (int)so[ri] - shift : 0) + gl;
+            e[i]  = active ? (int)so[ri + 1] - shift : 0;
         }
         T p[ROWS][U];
 #pragma unroll
@@ -273,17 +289,18 @@ __device__ __forceinline__ void split_rows_fixup(const CsrArgs<T>& a, T alpha, T
 }
 
 // ---------------- phase 2: per-row reduction out of shared memory ----------------------------------
-// sP[0 .. ne-ns) holds the tile's products, sOff[i] = rowOff[rs+i] - base - ns for i = 0 .. re-rs.
-template <typename T>
+// sP[0 .. ne-ns) holds the tile's products, sOff[i] - shift = rowOff[rs+i] - base - ns for i = 0 .. re-rs (the
+// tile / pipe kernels stage rebased offsets, shift = 0; the TMA-fed kernel stages the raw slice, shift = base + ns).
+template <typename T, typename OT, int BLOCK, int BAR_ID>
 __device__ __forceinline__ void tile_phase2(const CsrArgs<T>& a, int b, int rs, int ns, int re, int ne, const T* sP,
-                                            const int* sOff, T* sRed, T alpha, T beta) {
-    if (B200_CSR_ABLATE & 1) { if (sP[threadIdx.x] == T(1.2345)) a.y[0] = sP[0]; return; }
+                                            const OT* sOff, int shift, T* sRed, T alpha, T beta, int tid) {
+    if (B200_CSR_ABLATE & 1) { if (sP[tid] == T(1.2345)) a.y[0] = sP[0]; return; }
     const int cnt = ne - ns;
     bool head = false;
     int  head_end = 0;  // products [0, head_end) belong to the split row rs
-    if (rs < a.rows && sOff[0] < 0) {            // the tile starts inside row rs
+    if (rs < a.rows && (int)sOff[0] - shift < 0) {       // the tile starts inside row rs
         head = true;
-        const int o1 = re > rs ? sOff[1] : cnt;  // re == rs: the whole tile lies inside row rs
+        const int o1 = re > rs ? (int)sOff[1] - shift : cnt;  // re == rs: the whole tile lies inside row rs
         head_end = o1 < cnt ? o1 : cnt;
     }
     const int r_first = rs + (head ? 1 : 0);
@@ -291,33 +308,33 @@ __device__ __forceinline__ void tile_phase2(const CsrArgs<T>& a, int b, int rs, 
     int  tail_beg = cnt;               // products [tail_beg, cnt) belong to the split row re
     bool tail = false;
     if (re < a.rows && re >= r_first) {
-        const int o0 = sOff[re - rs];
+        const int o0 = (int)sOff[re - rs] - shift;
         if (cnt > o0) { tail = true; tail_beg = o0; }
     }
 
     if (nrows > 0) {
         const int body = tail_beg - head_end;
         const int avg2 = body / (2 * nrows);  // half the mean row length
-        if      (avg2 <= 1)  reduce_rows<T, 1,  RED_ROWS, RED_U, CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
-        else if (avg2 <= 2)  reduce_rows<T, 2,  RED_ROWS, RED_U, CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
-        else if (avg2 <= 4)  reduce_rows<T, 4,  RED_ROWS, RED_U, CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
-        else if (avg2 <= 8)  reduce_rows<T, 8,  RED_ROWS, RED_U, CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
-        else if (avg2 <= 16) reduce_rows<T, 16, RED_ROWS, RED_U, CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);
-        else                 reduce_rows<T, 32, 2, 8, CSR_BLOCK>(a, sP, sOff, rs, r_first, nrows, alpha, beta);  // long rows: 256 elements per batch
+        if      (avg2 <= 1)  reduce_rows<T, OT, 1, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 2)  reduce_rows<T, OT, 2, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 4)  reduce_rows<T, OT, 4, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 8)  reduce_rows<T, OT, 8, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 16) reduce_rows<T, OT, 16, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else                 reduce_rows<T, OT, 32, 2, 8, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);  // long rows: 256 elements per batch
     }
 
-    if (head) {  // block-uniform
-        const T hs = block_sum_range<T, CSR_BLOCK>(sP, 0, head_end, sRed);
-        if (threadIdx.x == 0) a.plan.head_part[b] = (double)hs;
+    if (head) {  // group-uniform
+        const T hs = block_sum_range<T, BLOCK, BAR_ID>(sP, 0, head_end, sRed, tid);
+        if (tid == 0) a.plan.head_part[b] = (double)hs;
     }
-    if (tail) {  // block-uniform
-        const T ts = block_sum_range<T, CSR_BLOCK>(sP, tail_beg, cnt, sRed);
-        if (threadIdx.x == 0) a.plan.tail_part[b] = (double)ts;
+    if (tail) {  // group-uniform
+        const T ts = block_sum_range<T, BLOCK, BAR_ID>(sP, tail_beg, cnt, sRed, tid);
+        if (tid == 0) a.plan.tail_part[b] = (double)ts;
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(CSR_BLOCK, B200_CSR_MIN_CTAS) csr_tile_kernel(const CsrArgs<T> a) {
+__global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel(const CsrArgs<T> a) {
     __shared__ T   sP[CSR_SMEM_ELEMS];
     __shared__ int sOff[CSR_SMEM_ELEMS + 1];   // rowOff[rs .. re] - base - ns: a tile spans < CSR_SMEM_ELEMS rows
     __shared__ T   sRed[CSR_BLOCK / 32];
@@ -374,9 +391,23 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_CSR_MIN_CTAS) csr_tile_kernel(
     __syncthreads();
     TRACE_STAMP(a, b, 1);
 
-    tile_phase2<T>(a, b, rs, ns, re, ne, sP, sOff, sRed, alpha, beta);
+    tile_phase2<T, int, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
     TRACE_STAMP(a, b, 2);
-    split_rows_fixup<T>(a, alpha, beta);
+}
+
+// One-CTA-per-tile launches cannot afford an exit protocol in every CTA: their split rows are combined by this
+// small second launch instead (same arithmetic, same fixed order as split_rows_fixup).
+template <typename T>
+__global__ void __launch_bounds__(256) csr_fixup_kernel(const CsrArgs<T> a) {
+    const T alpha = a.s.a(), beta = a.s.b();
+    const int nsplit = a.plan.ctl[1];
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < nsplit; i += (int)(gridDim.x * blockDim.x)) {
+        const int4 sr = a.plan.split[i];
+        double sum = __ldcg(a.plan.tail_part + sr.y);
+        for (int b = sr.y + 1; b <= sr.z; b++) sum += __ldcg(a.plan.head_part + b);
+        T* yp = a.y + sr.x;
+        *yp = axpby(alpha, (T)sum, beta, yp);
+    }
 }
 
 // ================================================================================================
@@ -418,7 +449,7 @@ __device__ __forceinline__ void pipe_issue_loads(const CsrArgs<T>& a, int2 st, i
 }
 
 template <typename T>
-__global__ void __launch_bounds__(CSR_BLOCK, B200_CSR_MIN_CTAS) csr_pipe_kernel(const CsrArgs<T> a, int num_tiles) {
+__global__ void __launch_bounds__(CSR_BLOCK, B200_PIPE_MIN_CTAS) csr_pipe_kernel(const CsrArgs<T> a, int num_tiles) {
     __shared__ T   sP[CSR_SMEM_ELEMS];
     __shared__ int sOff[CSR_SMEM_ELEMS + 1];
     __shared__ T   sRed[CSR_BLOCK / 32];
@@ -473,7 +504,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_CSR_MIN_CTAS) csr_pipe_kernel(
 
         if (has_next) pipe_issue_loads(a, nst, nen, t);   // block-uniform; overlaps phase 2 below
 
-        tile_phase2<T>(a, b, rs, ns, re, ne, sP, sOff, sRed, alpha, beta);
+        tile_phase2<T, int, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
         TRACE_STAMP(a, b, 2);
         if (!has_next) break;
         __syncthreads();                                   // sP / sOff are free again
@@ -482,8 +513,373 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_CSR_MIN_CTAS) csr_pipe_kernel(
     split_rows_fixup<T>(a, alpha, beta);
 }
 
+// ================================================================================================
+// Warp-specialised, TMA-fed variant (B200_CSR_KERNEL == 2).
+//
+// Measured on the tile / pipe kernels: the three costs of a tile -- streaming val/col from HBM, gathering x through
+// L1TEX, reducing the products out of shared memory -- ADD UP when one set of warps performs them one after the
+// other (stream-only 31 us, +gathers 62 us, +reduction 99 us on R-MAT 1M), although they use different resources.
+// Here each resource gets its own agents inside one persistent CTA, decoupled by a ring of STAGES tile buffers in
+// shared memory and mbarriers:
+//
+//   producer warp   : cp.async.bulk (TMA, 1-D) of the tile's col_ind / val / rowOff slices global -> shared,
+//                     complete_tx on full[s].  Runs STAGES tiles ahead:
+//                     HBM stays busy no matter what the other warps wait for.
+//   gather warps    : wait full[s]; read col from shared, gather x (the only L1TEX-heavy part), multiply with val
+//                     from shared, store the product in place; arrive on prod[s].
+//   reduce groups   : RGROUPS groups of RWARPS warps, tile i belongs to group i % RGROUPS; wait prod[s]; per-row
+//                     reduction out of shared memory (same code as the other kernels), write y; arrive on empty[s].
+// ================================================================================================
+#ifndef B200_WS_GATHER_WARPS
+#define B200_WS_GATHER_WARPS 8
+#endif
+#ifndef B200_WS_REDUCE_WARPS
+#define B200_WS_REDUCE_WARPS 4
+#endif
+#ifndef B200_WS_REDUCE_GROUPS
+#define B200_WS_REDUCE_GROUPS 2
+#endif
+#ifndef B200_WS_STAGES
+#define B200_WS_STAGES 4
+#endif
+#ifndef B200_WS_MIN_CTAS
+#define B200_WS_MIN_CTAS 1
+#endif
+#ifndef B200_WS_GATHER_UNROLL
+#define B200_WS_GATHER_UNROLL 8
+#endif
+constexpr int WS_GW = B200_WS_GATHER_WARPS, WS_RW = B200_WS_REDUCE_WARPS, WS_RG = B200_WS_REDUCE_GROUPS;
+constexpr int WS_STAGES = B200_WS_STAGES;
+constexpr int WS_THREADS = 32 * (1 + WS_GW + WS_RW * WS_RG);
+constexpr int WS_ELEMS = (CSR_SMEM_ELEMS + 32 + 3) & ~3;        // a tile's [al, ne) range: < SMEM_ELEMS + 32 elements
+constexpr int WS_OFFS  = (CSR_SMEM_ELEMS + 1 + 3 + 3) & ~3;     // rowOff[rs&~3 .. re]: <= SMEM_ELEMS + 3 entries
+
+template <typename T>
+struct WsStage {
+    static constexpr size_t col_bytes = (size_t)WS_ELEMS * sizeof(int);
+    static constexpr size_t val_bytes = (size_t)WS_ELEMS * sizeof(T);
+    static constexpr size_t off_bytes = (size_t)WS_OFFS * sizeof(int);
+    static constexpr size_t bytes = (col_bytes + val_bytes + off_bytes + 127) / 128 * 128;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WS_THREADS, B200_WS_MIN_CTAS) csr_ws_kernel(const CsrArgs<T> a, int num_tiles) {
+    extern __shared__ __align__(128) unsigned char ws_smem[];
+    __shared__ uint64_t bar_full[WS_STAGES], bar_off[WS_STAGES], bar_prod[WS_STAGES], bar_empty[WS_STAGES];
+    __shared__ T sRed[WS_RG][WS_RW];
+
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < WS_STAGES; s++) {
+            mbar_init(&bar_full[s], 1);        // producer's arrive.expect_tx (+ the TMA bytes)
+            mbar_init(&bar_off[s], 1);         // producer, after the rowOff slice is in shared memory
+            mbar_init(&bar_prod[s], WS_GW);    // one arrive per gather warp
+            mbar_init(&bar_empty[s], WS_RW);   // one arrive per warp of the reduce group that owned the tile
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const T alpha = a.s.a(), beta = a.s.b();
+
+    auto stage_col = [&](int s) { return (int*)(ws_smem + (size_t)s * WsStage<T>::bytes); };
+    auto stage_val = [&](int s) { return (T*)(ws_smem + (size_t)s * WsStage<T>::bytes + WsStage<T>::col_bytes); };
+    auto stage_off = [&](int s) {
+        return (int*)(ws_smem + (size_t)s * WsStage<T>::bytes + WsStage<T>::col_bytes + WsStage<T>::val_bytes);
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer ------------------------------------------------
+        int i = 0;
+        for (int b = blockIdx.x; b < num_tiles; b += gridDim.x, i++) {
+            const int s = i % WS_STAGES, n = i / WS_STAGES;
+            if (n > 0) mbar_wait(&bar_empty[s], (uint32_t)((n - 1) & 1));
+            const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
+            const int rs = st.x, ns = st.y, re = en.x, ne = en.y;
+            const int al = ns & ~31, span = ne - al;
+            int copied = (span + 3) & ~3;                       // whole 16-byte units ...
+            if (copied > a.nnz - al) copied = (a.nnz - al) & ~3;  // ... that stay inside the arrays
+            // rowOff[rs4 .. re] (rs4 = rs rounded down to a 16-byte boundary), raw values
+            const int rs4 = rs & ~3;
+            int ocopied = (re - rs4 + 1 + 3) & ~3;
+            if (ocopied > a.rows + 1 - rs4) ocopied = (a.rows + 1 - rs4) & ~3;
+            int* so = stage_off(s);
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive_expect_tx(&bar_full[s], (uint32_t)(copied * (sizeof(int) + sizeof(T)) + ocopied * sizeof(int)));
+                if (copied > 0) {
+                    tma_bulk_g2s(stage_col(s), a.col + al, (uint32_t)(copied * sizeof(int)), &bar_full[s]);
+                    tma_bulk_g2s(stage_val(s), a.val + al, (uint32_t)(copied * sizeof(T)), &bar_full[s]);
+                }
+                if (ocopied > 0) tma_bulk_g2s(so, a.off + rs4, (uint32_t)(ocopied * sizeof(int)), &bar_full[s]);
+            }
+            for (int j = ocopied + lane; j < re - rs4 + 1; j += 32) so[j] = __ldg(a.off + rs4 + j);   // <= 3 entries, last tile only
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_off[s]);
+        }
+    } else if (warp <= WS_GW) {
+        // ------------------------------------------------ gather warps --------------------------------------------
+        const int gtid = tid - 32;
+        constexpr int GT = WS_GW * 32, UNR = B200_WS_GATHER_UNROLL;
+        int i = 0;
+        for (int b = blockIdx.x; b < num_tiles; b += gridDim.x, i++) {
+            const int s = i % WS_STAGES, n = i / WS_STAGES;
+            const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
+            const int ns = st.y, ne = en.y;
+            const int al = ns & ~31, lead = ns - al, span = ne - al;
+            int copied = (span + 3) & ~3;
+            if (copied > a.nnz - al) copied = (a.nnz - al) & ~3;
+            const int* sc = stage_col(s);
+            T*         sv = stage_val(s);
+            mbar_wait(&bar_full[s], (uint32_t)(n & 1));
+            for (int e0 = 0; e0 < span; e0 += GT * UNR) {
+                int c[UNR];
+                T   xv[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const int e = e0 + u * GT + gtid;
+                    const bool live = e >= lead && e < span;
+                    c[u] = !live ? a.base : (e < copied ? sc[e] : ldg_stream(a.col + al + e));
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const int e = e0 + u * GT + gtid;
+                    const bool live = e >= lead && e < span;
+                    xv[u] = (live && !(B200_CSR_ABLATE & 2)) ? __ldg(a.x + (c[u] - a.base)) : T(0);
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const int e = e0 + u * GT + gtid;
+                    if (e >= lead && e < span) {
+                        const T v = e < copied ? sv[e] : ldg_stream(a.val + al + e);
+                        sv[e] = v * xv[u];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_prod[s]);
+        }
+    } else {
+        // ------------------------------------------------ reduce groups -------------------------------------------
+        const int rwarp = warp - 1 - WS_GW;                 // 0 .. RW*RG-1
+        const int grp = rwarp / WS_RW, rtid = tid - 32 * (1 + WS_GW) - grp * (WS_RW * 32);
+        int i = 0;
+        for (int b = blockIdx.x; b < num_tiles; b += gridDim.x, i++) {
+            if (i % WS_RG != grp) continue;
+            const int s = i % WS_STAGES, n = i / WS_STAGES;
+            const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
+            const int rs = st.x, ns = st.y, re = en.x, ne = en.y;
+            const int lead = ns - (ns & ~31);
+            mbar_wait(&bar_off[s], (uint32_t)(n & 1));
+            mbar_wait(&bar_full[s], (uint32_t)(n & 1));
+            mbar_wait(&bar_prod[s], (uint32_t)(n & 1));
+            const int* so = stage_off(s) + (rs - (rs & ~3));
+            const int shift = a.base + ns;
+            if (grp == 0)
+                tile_phase2<T, int, WS_RW * 32, 1>(a, b, rs, ns, re, ne, stage_val(s) + lead, so, shift, sRed[0], alpha, beta, rtid);
+            else if (grp == 1)
+                tile_phase2<T, int, WS_RW * 32, 2>(a, b, rs, ns, re, ne, stage_val(s) + lead, so, shift, sRed[WS_RG > 1 ? 1 : 0], alpha, beta, rtid);
+            else if (grp == 2)
+                tile_phase2<T, int, WS_RW * 32, 3>(a, b, rs, ns, re, ne, stage_val(s) + lead, so, shift, sRed[WS_RG > 2 ? 2 : 0], alpha, beta, rtid);
+            else
+                tile_phase2<T, int, WS_RW * 32, 4>(a, b, rs, ns, re, ne, stage_val(s) + lead, so, shift, sRed[WS_RG > 3 ? 3 : 0], alpha, beta, rtid);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[s]);
+        }
+    }
+    split_rows_fixup<T>(a, alpha, beta);
+}
+
+// ================================================================================================
+// Row-wise variant (B200_CSR_KERNEL == 3): the tile partition bounds and balances the work, but inside a tile the
+// products never touch shared memory.  A group of G lanes (G picked per tile from its mean row length) owns ROWS rows
+// at a time: it reads their val/col segments straight from global memory (neighbouring groups own neighbouring rows,
+// so a warp-level load still covers one contiguous span), gathers x, accumulates in registers and finishes with one
+// shuffle tree per row.  Rationale (measured): the SM's L1TEX pipe is the bottleneck resource on scattered matrices
+// and serves gathers, shared-memory accesses and shuffles strictly one after the other, so every STS/LDS of a product
+// costs as much as a gather; this variant spends the pipe on gathers + log2(G) shuffles per ROW only.
+// ================================================================================================
+#ifndef B200_RW_ROWS
+#define B200_RW_ROWS 4
+#endif
+#ifndef B200_RW_U
+#define B200_RW_U 2
+#endif
+
+template <typename T, int G, int ROWS, int U, int BLOCK>
+__device__ __forceinline__ void rowwise_rows(const CsrArgs<T>& a, int r_first, int nrows, T alpha, T beta, int tid) {
+    constexpr int GROUPS = BLOCK / G;
+    const int gid = tid / G, gl = tid % G;
+    const int* off = a.off + r_first;
+    const int* colp = a.col - a.base;     // off[] values are base-indexed positions
+    const T*   valp = a.val - a.base;
+    const T*   xp   = a.x - a.base;
+    for (int r0 = 0; r0 < nrows; r0 += GROUPS * ROWS) {
+        int k0[ROWS], e[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; i++) {
+            const int ri = r0 + i * GROUPS + gid;
+            const bool active = ri < nrows;
+            k0[i] = (active ? __ldg(off + ri) : 0) + gl;
+            e[i]  = active ? __ldg(off + ri + 1) : 0;
+        }
+        int c[ROWS][U];
+        T   v[ROWS][U];
+#pragma unroll
+        for (int i = 0; i < ROWS; i++)
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int k = k0[i] + u * G;
+                const bool live = k < e[i];
+                c[i][u] = live ? ldg_stream(colp + k) : a.base;
+                v[i][u] = live ? ldg_stream(valp + k) : T(0);
+            }
+        T sum[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; i++) {
+            T xv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) xv[u] = (k0[i] + u * G < e[i]) ? __ldg(xp + c[i][u]) : T(0);
+            sum[i] = v[i][0] * xv[0];
+#pragma unroll
+            for (int u = 1; u < U; u++) sum[i] += v[i][u] * xv[u];
+        }
+#pragma unroll
+        for (int i = 0; i < ROWS; i++) {                        // rows longer than U*G: batches of U loads in flight
+            for (int kb = k0[i] + U * G; kb < e[i]; kb += U * G) {
+                int cc[U];
+                T   vv[U], xx[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const bool live = kb + u * G < e[i];
+                    cc[u] = live ? ldg_stream(colp + kb + u * G) : a.base;
+                    vv[u] = live ? ldg_stream(valp + kb + u * G) : T(0);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) xx[u] = (kb + u * G < e[i]) ? __ldg(xp + cc[u]) : T(0);
+#pragma unroll
+                for (int u = 0; u < U; u++) sum[i] += vv[u] * xx[u];
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < ROWS; i++) sum[i] += __shfl_down_sync(0xffffffffu, sum[i], o, G);
+        if (gl == 0) {
+#pragma unroll
+            for (int i = 0; i < ROWS; i++) {
+                const int ri = r0 + i * GROUPS + gid;
+                if (ri < nrows) {
+                    T* yp = a.y + r_first + ri;
+                    *yp = axpby(alpha, sum[i], beta, yp);
+                }
+            }
+        }
+    }
+}
+
+// Sum val[k]*x[col[k]] for k in [lo, hi) (0-based positions) with the whole CTA; result valid on thread 0.
+template <typename T, int BLOCK>
+__device__ __forceinline__ T block_dot_range(const CsrArgs<T>& a, int lo, int hi, T* sRed, int tid) {
+    T s = T(0);
+    for (int k = lo + tid; k < hi; k += 4 * BLOCK) {
+        int cc[4];
+        T   vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool live = k + u * BLOCK < hi;
+            cc[u] = live ? ldg_stream(a.col + k + u * BLOCK) : a.base;
+            vv[u] = live ? ldg_stream(a.val + k + u * BLOCK) : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) s += (k + u * BLOCK < hi) ? vv[u] * __ldg(a.x + (cc[u] - a.base)) : T(0);
+    }
+    s = warp_sum(s);
+    __syncthreads();
+    if ((tid & 31) == 0) sRed[tid >> 5] = s;
+    __syncthreads();
+    T tot = T(0);
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 0; w < BLOCK / 32; w++) tot += sRed[w];
+    }
+    return tot;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CSR_BLOCK, B200_RW_MIN_CTAS) csr_rowwise_kernel(const CsrArgs<T> a) {
+    __shared__ T sRed[CSR_BLOCK / 32];
+    const int  b  = blockIdx.x, tid = (int)threadIdx.x;
+    const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
+    const int  rs = st.x, ns = st.y, re = en.x, ne = en.y;
+    const T alpha = a.s.a(), beta = a.s.b();
+
+    bool head = false;
+    int  head_end = ns;                      // non-zeros [ns, head_end) belong to the split row rs
+    if (rs < a.rows && ns > __ldg(a.off + rs) - a.base) {
+        head = true;
+        const int o1 = __ldg(a.off + rs + 1) - a.base;
+        head_end = o1 < ne ? o1 : ne;
+    }
+    const int r_first = rs + (head ? 1 : 0);
+    const int nrows   = re - r_first;
+    bool tail = false;
+    int  tail_beg = ne;                      // non-zeros [tail_beg, ne) belong to the split row re
+    if (re < a.rows && re >= r_first) {
+        const int o0 = __ldg(a.off + re) - a.base;
+        if (ne > o0) { tail = true; tail_beg = o0; }
+    }
+    if (nrows > 0) {
+        const int body = tail_beg - head_end;
+        const int avg2 = body / (2 * nrows);
+        if      (avg2 <= 1)  rowwise_rows<T, 1,  B200_RW_ROWS, B200_RW_U, CSR_BLOCK>(a, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 2)  rowwise_rows<T, 2,  B200_RW_ROWS, B200_RW_U, CSR_BLOCK>(a, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 4)  rowwise_rows<T, 4,  B200_RW_ROWS, B200_RW_U, CSR_BLOCK>(a, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 8)  rowwise_rows<T, 8,  B200_RW_ROWS, B200_RW_U, CSR_BLOCK>(a, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 16) rowwise_rows<T, 16, B200_RW_ROWS, B200_RW_U, CSR_BLOCK>(a, r_first, nrows, alpha, beta, tid);
+        else                 rowwise_rows<T, 32, 2, 4, CSR_BLOCK>(a, r_first, nrows, alpha, beta, tid);
+    }
+    if (head) {
+        const T hs = block_dot_range<T, CSR_BLOCK>(a, ns, head_end, sRed, tid);
+        if (tid == 0) a.plan.head_part[b] = (double)hs;
+    }
+    if (tail) {
+        const T ts = block_dot_range<T, CSR_BLOCK>(a, tail_beg, ne, sRed, tid);
+        if (tid == 0) a.plan.tail_part[b] = (double)ts;
+    }
+}
+
 // SMs x resident CTAs per SM of a kernel on the current device (cached per device / kernel).
-static int resident_ctas(const void* kernel) {
+static int resident_ctas(const void* kernel, int block = CSR_BLOCK, size_t dyn_smem = 0) {
     struct Entry { int dev; const void* k; int n; };
     static Entry cache[32];
     static int ncache = 0;
@@ -493,7 +889,8 @@ static int resident_ctas(const void* kernel) {
         if (cache[i].dev == dev && cache[i].k == kernel) return cache[i].n;
     int sms = 148, per = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, CSR_BLOCK, 0);
+    if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, block, dyn_smem);
     if (per < 1) per = 1;
     const int n = sms * per;
     if (ncache < 32) cache[ncache++] = Entry{dev, kernel, n};
@@ -516,13 +913,32 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
 #ifdef B200_CSR_TRACE
     a.trace = g_trace_ptr;
 #endif
-#if B200_CSR_KERNEL == 0
-    csr_tile_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
-#else
-    int64_t grid = (int64_t)resident_ctas((const void*)csr_pipe_kernel<T>);
-    if (grid > nt) grid = nt;
-    csr_pipe_kernel<T><<<(unsigned)grid, CSR_BLOCK, 0, stream>>>(a, (int)nt);
-#endif
+    // Which kernel?  Measured on B200 (profiles/): matrices with short rows (stencils, < 12 non-zeros per row on
+    // average) run fastest on the persistent software-pipelined kernel; longer / skewed rows on one CTA per tile.
+    // B200SPMV_CSR_KERNEL=tile|pipe|ws|rowwise overrides (experiments), as does -DB200_CSR_KERNEL at build time.
+    int mode = B200_CSR_KERNEL;
+    if (mode < 0) {
+        const char* e = getenv("B200SPMV_CSR_KERNEL");   // read per call (~0.1 us) so tests can switch kernels
+        const int env_mode = !e ? -1 : !strcmp(e, "tile") ? 0 : !strcmp(e, "pipe") ? 1 : !strcmp(e, "ws") ? 2 : !strcmp(e, "rowwise") ? 3 : -1;
+        mode = env_mode >= 0 ? env_mode : (nnz >= 12 * rows ? 0 : 1);
+    }
+    if (mode == 2 && (((uintptr_t)col | (uintptr_t)val | (uintptr_t)off) & 15) != 0) mode = 1;   // TMA needs 16 B alignment
+    if (mode == 0) {
+        csr_tile_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+        csr_fixup_kernel<T><<<8, 256, 0, stream>>>(a);
+    } else if (mode == 3) {
+        csr_rowwise_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+        csr_fixup_kernel<T><<<8, 256, 0, stream>>>(a);
+    } else if (mode == 2) {
+        const size_t dyn = (size_t)WS_STAGES * WsStage<T>::bytes;
+        int64_t grid = (int64_t)resident_ctas((const void*)csr_ws_kernel<T>, WS_THREADS, dyn);
+        if (grid > nt) grid = nt;
+        csr_ws_kernel<T><<<(unsigned)grid, WS_THREADS, dyn, stream>>>(a, (int)nt);
+    } else {
+        int64_t grid = (int64_t)resident_ctas((const void*)csr_pipe_kernel<T>);
+        if (grid > nt) grid = nt;
+        csr_pipe_kernel<T><<<(unsigned)grid, CSR_BLOCK, 0, stream>>>(a, (int)nt);
+    }
     return (int)cudaGetLastError();
 }
 
@@ -546,6 +962,18 @@ void b200spmv_csr_plan_params(int32_t* tile_items, int32_t* long_row, int32_t* b
 }
 
 size_t b200spmv_csr_plan_tiles_offset(void) { return PLAN_HEADER_BYTES; }
+
+size_t b200spmv_csr_plan_ctl_offset(int64_t rows, int64_t nnz) {
+    PlanView v;
+    plan_layout(csr_num_tiles(rows, nnz), nullptr, &v);
+    return (size_t)((char*)v.ctl - (char*)nullptr);
+}
+
+size_t b200spmv_csr_plan_split_offset(int64_t rows, int64_t nnz) {
+    PlanView v;
+    plan_layout(csr_num_tiles(rows, nnz), nullptr, &v);
+    return (size_t)((char*)v.split - (char*)nullptr);
+}
 
 int b200spmv_csr_analyze(void* stream, int64_t rows, int64_t nnz, const void* row_offsets, int32_t base,
                          void* workspace) {

@@ -76,6 +76,8 @@ def shim(build_if_missing: bool = False) -> C.CDLL:
         lib.b200spmv_coo_workspace_bytes.restype = C.c_size_t
         lib.b200spmv_sell_workspace_bytes.restype = C.c_size_t
         lib.b200spmv_csr_plan_tiles_offset.restype = C.c_size_t
+        lib.b200spmv_csr_plan_ctl_offset.restype = C.c_size_t
+        lib.b200spmv_csr_plan_split_offset.restype = C.c_size_t
         lib.b200spmv_csr_num_tiles.restype = C.c_int64
         lib.b200spmv_version.restype = C.c_char_p
         _shim = lib

@@ -53,6 +53,10 @@ B200SPMV_EXPORT int    b200spmv_csr_mv(void* stream, int dtype, int64_t rows, in
 B200SPMV_EXPORT int64_t b200spmv_csr_num_tiles(int64_t rows, int64_t nnz);
 B200SPMV_EXPORT void    b200spmv_csr_plan_params(int32_t* tile_items, int32_t* long_row, int32_t* block_threads);
 B200SPMV_EXPORT size_t  b200spmv_csr_plan_tiles_offset(void);
+/* byte offsets inside the workspace of the control words {finished CTAs, number of split rows} and of the split-row
+ * list (int4 {row, first covering tile, last covering tile, 0}) */
+B200SPMV_EXPORT size_t  b200spmv_csr_plan_ctl_offset(int64_t rows, int64_t nnz);
+B200SPMV_EXPORT size_t  b200spmv_csr_plan_split_offset(int64_t rows, int64_t nnz);
 
 /* COO (row-sorted or not).  Replaces cusparseSpMV for cusparseCreateCoo descriptors
  * (cuSPARSE/spmv_coo/spmv_coo_example.c:86-104). */

@@ -59,3 +59,26 @@ def check_partition(tiles, off, base, tile_items, long_row):
         assert np.all(off[rl + 1] - off[rl] >= long_row)
         assert np.all((n[mid] > off[rl]) & (n[mid] <= off[rl + 1]))
     return True
+
+
+def split_rows(tiles, off, base, tile_items):
+    """Rows cut by a tile boundary, as (row, first covering tile b1, last covering tile b2), sorted by row.
+
+    Restates the split list that csr_partition_kernel registers: boundary b lies strictly inside row r
+    (tiles[b].nnz > off[r]); b1 = g(r) // tile_items, b2 = (g(r) + len(r)) // tile_items with g(r) = r + off[r];
+    the row is registered by its first cut, b == b1 + 1.
+    """
+    off = np.asarray(off, np.int64) - base
+    rows = off.size - 1
+    t = tiles.astype(np.int64)
+    r, n = t[:, 0], t[:, 1]
+    mid = (r < rows) & (n > off[np.minimum(r, rows)])
+    out = []
+    for b in np.nonzero(mid)[0]:
+        rr = int(r[b])
+        g0 = rr + int(off[rr])
+        b1 = g0 // tile_items
+        b2 = (g0 + int(off[rr + 1] - off[rr])) // tile_items
+        if b == b1 + 1:
+            out.append((rr, b1, b2))
+    return sorted(out)

@@ -52,6 +52,35 @@ if os.environ.get("SWEEP_SET") == "red":
             VARIANTS[f"pipe_r{rr}u{ru}_occ{o}"] = dict(TILE=2048, LONG=512, BLOCK=256, BATCH=4, MIN=o, KERNEL=1, OFFS=4, RR=rr, RU=ru)
         VARIANTS[f"tile_r{rr}u{ru}_occ5"] = dict(TILE=2048, LONG=512, BLOCK=256, BATCH=4, MIN=5, KERNEL=0, RR=rr, RU=ru)
         VARIANTS[f"pipe1024_r{rr}u{ru}_occ8"] = dict(TILE=1024, LONG=256, BLOCK=128, BATCH=4, MIN=8, KERNEL=1, OFFS=4, RR=rr, RU=ru)
+if os.environ.get("SWEEP_SET") == "ws":
+    VARIANTS = {}
+    #            tile  long gw rw rg st un ctas
+    for cfg in [(2048, 512, 8, 4, 2, 4, 8, 1), (2048, 512, 4, 4, 1, 2, 8, 2), (2048, 512, 4, 4, 1, 3, 8, 2),
+                (1024, 256, 4, 4, 1, 3, 8, 3), (1024, 256, 4, 4, 1, 3, 8, 4), (1024, 256, 4, 2, 1, 3, 8, 4),
+                (1024, 256, 2, 2, 1, 3, 8, 6), (1024, 256, 4, 2, 1, 2, 8, 5), (512, 128, 2, 2, 1, 3, 8, 8),
+                (1024, 256, 4, 4, 1, 4, 8, 3)]:
+        t, l, gw, rw, rg, st, un, ct = cfg
+        VARIANTS[f"ws_t{t}_g{gw}_r{rw}x{rg}_s{st}_c{ct}"] = dict(TILE=t, LONG=l, BLOCK=256, BATCH=4, MIN=4, WS=cfg[2:])
+if os.environ.get("SWEEP_SET") == "small":
+    VARIANTS = {}
+    for (t, l, bl, k, o) in [(512, 128, 128, 6, 16), (512, 128, 128, 3, 16), (512, 128, 128, 6, 12), (768, 256, 128, 9, 12),
+                             (1024, 256, 128, 11, 12), (1024, 256, 128, 4, 12), (512, 128, 64, 11, 24), (256, 64, 64, 6, 32),
+                             (1024, 256, 256, 6, 6), (2048, 512, 256, 4, 5), (384, 128, 128, 5, 16), (640, 128, 128, 7, 14)]:
+        VARIANTS[f"tile_t{t}_l{l}_b{bl}_k{k}_occ{o}"] = dict(TILE=t, LONG=l, BLOCK=bl, BATCH=k, MIN=o, KERNEL=0)
+if os.environ.get("SWEEP_SET") == "rw":
+    VARIANTS = {}
+    for (t, l, bl, o, rr, ru) in [(2048, 512, 256, 4, 4, 2), (2048, 512, 256, 6, 2, 2), (2048, 512, 256, 5, 4, 1), (2048, 512, 256, 8, 2, 1),
+                                  (1024, 256, 128, 8, 4, 2), (1024, 256, 128, 12, 2, 2), (1024, 256, 256, 6, 2, 2), (4096, 1024, 256, 4, 4, 2),
+                                  (2048, 512, 256, 4, 2, 4), (2048, 512, 128, 8, 4, 2), (512, 128, 128, 12, 2, 2), (2048, 512, 256, 3, 4, 4)]:
+        VARIANTS[f"rw_t{t}_b{bl}_occ{o}_r{rr}u{ru}"] = dict(TILE=t, LONG=l, BLOCK=bl, BATCH=4, MIN=o, KERNEL=3, RW=(rr, ru))
+if os.environ.get("SWEEP_SET") == "final":
+    VARIANTS = {
+        "tile_occ5": dict(TILE=2048, LONG=512, BLOCK=256, BATCH=4, MIN=5, KERNEL=0, RR=2, RU=2),
+        "tile_occ6": dict(TILE=2048, LONG=512, BLOCK=256, BATCH=4, MIN=6, KERNEL=0, RR=2, RU=2),
+        "pipe_occ3": dict(TILE=2048, LONG=512, BLOCK=256, BATCH=4, MIN=3, KERNEL=1, OFFS=4, RR=2, RU=2),
+        "pipe_occ4": dict(TILE=2048, LONG=512, BLOCK=256, BATCH=4, MIN=4, KERNEL=1, OFFS=4, RR=2, RU=4),
+        "rw_b128_occ8": dict(TILE=2048, LONG=512, BLOCK=128, BATCH=4, MIN=8, KERNEL=3, RW=(4, 2)),
+    }
 if os.environ.get("SWEEP_SET") == "ablate":
     VARIANTS = dict(ABL, t2048_b256_k4_occ6=VARIANTS["t2048_b256_k4_occ6"])
 
@@ -59,6 +88,13 @@ if os.environ.get("SWEEP_SET") == "ablate":
 def flags(v):
     if "ABL" in v:
         return flags({k: x for k, x in v.items() if k != "ABL"}) + [f"-DB200_CSR_ABLATE={v['ABL']}"]
+    if "RW" in v:
+        return flags({k: x for k, x in v.items() if k != "RW"}) + [f"-DB200_RW_ROWS={v['RW'][0]}", f"-DB200_RW_U={v['RW'][1]}"]
+    if "WS" in v:
+        gw, rw, rg, st, un, ct = v["WS"]
+        return flags({k: x for k, x in v.items() if k != "WS"}) + ["-DB200_CSR_KERNEL=2", f"-DB200_WS_GATHER_WARPS={gw}",
+                f"-DB200_WS_REDUCE_WARPS={rw}", f"-DB200_WS_REDUCE_GROUPS={rg}", f"-DB200_WS_STAGES={st}", f"-DB200_WS_GATHER_UNROLL={un}",
+                f"-DB200_WS_MIN_CTAS={ct}"]
     if "RR" in v:
         return flags({k: x for k, x in v.items() if k not in ("RR", "RU")}) + [f"-DB200_CSR_RED_ROWS={v['RR']}", f"-DB200_CSR_RED_U={v['RU']}"]
     if "KERNEL" in v:
@@ -75,7 +111,7 @@ def build():
         out = os.path.join(VDIR, f"libb200spmv_{tag}.so")
         b.build_native(extra_flags=flags(v), out_path=out, tag="v_" + tag)
         log = open(os.path.join(ROOT, "cudalibrarysamples_b200", "build", "v_" + tag, "build.log")).read()
-        i = max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
+        i = log.find("csr_rowwise_kernelIdEE") if "RW" in v else log.find("csr_ws_kernelIdEE") if "WS" in v else max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
         regs = log[i:i + 400].split("Used ")[1].split(",")[0] if i >= 0 else "?"
         print(tag, regs)
 
@@ -84,7 +120,7 @@ def make_workload(name):
     import torch
     from cudalibrarysamples_b200 import workloads as W
     if name.startswith("rmat"):
-        rows = {"rmat1m": 1_000_000, "rmat10m": 10_000_000, "rmat4m": 4_000_000}[name]
+        rows = {"rmat1m": 1_000_000, "rmat10m": 10_000_000, "rmat4m": 4_000_000, "rmat250k": 250_000}[name]
         off, col, val = W.rmat_csr(rows)
     elif name == "uniform1m":
         rows = 1_000_000

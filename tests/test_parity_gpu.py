@@ -199,6 +199,50 @@ def test_csr_base_one(cs, b200, closed, dtype):
     assert relerr(got.cpu().numpy(), lib.cpu().numpy()) < TOL[dtype]
 
 
+@pytest.fixture(params=["tile", "pipe", "ws", "rowwise"])
+def csr_kernel(request):
+    """Every CSR kernel variant of the library must give the same answers (B200SPMV_CSR_KERNEL picks one)."""
+    old = os.environ.get("B200SPMV_CSR_KERNEL")
+    os.environ["B200SPMV_CSR_KERNEL"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("B200SPMV_CSR_KERNEL", None)
+    else:
+        os.environ["B200SPMV_CSR_KERNEL"] = old
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_every_csr_kernel_variant(cs, b200, csr_kernel, dtype):
+    rows = 50000
+    off, col, val, x, y0 = rmat_case(rows, 16, dtype, 121)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    for alpha, beta in [(1.0, 0.0), (-1.0, 1.0)]:
+        want = O.spmv_csr(off, col, val, x, y0, alpha, beta)
+        got = run(cs, b200, "csr", rows, rows, arrays, dev(x), dev(y0), alpha, beta)
+        assert relerr(got.cpu().numpy(), want) < TOL[dtype], (csr_kernel, alpha, beta)
+        again = run(cs, b200, "csr", rows, rows, arrays, dev(x), dev(y0), alpha, beta)
+        assert torch.equal(got, again)
+    # short rows + base 1 + no preprocess
+    off, col, val = O.gen_stencil5(200)
+    n = 200 * 200
+    xs, ys = O.uniform(5, n), O.uniform(6, n)
+    arrays = dict(off=dev(off + 1), col=dev(col + 1), val=dev(val))
+    got = run(cs, b200, "csr", n, n, arrays, dev(xs), dev(ys), 0.75, 0.5, base=1, preprocess=False)
+    assert relerr(got.cpu().numpy(), O.spmv_csr(off, col, val, xs, ys, 0.75, 0.5)) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["single_huge_row", "huge_then_tiny", "alternating", "all_empty", "trailing_empty"])
+def test_every_csr_kernel_variant_edge_profiles(cs, b200, csr_kernel, name):
+    lens = EDGE[name]
+    rows, cols = lens.size, 120000
+    off, col, val = lens_to_csr(lens, cols, 3)
+    x, y0 = O.uniform(1, cols), O.uniform(2, rows)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    want = O.spmv_csr(off, col, val, x, y0, -2.0, 0.5)
+    got = run(cs, b200, "csr", rows, cols, arrays, dev(x), dev(y0), -2.0, 0.5).cpu().numpy()
+    assert relerr(got, want) < 1e-12, (csr_kernel, name)
+
+
 def lens_to_csr(lens, cols, seed, dtype=np.float64):
     rng = np.random.default_rng(seed)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
@@ -405,6 +449,15 @@ def test_partition_is_bit_exact(cs, b200, case, base):
     want = csr_partition(off, base, t.value, l.value)
     assert np.array_equal(got, want)
     assert check_partition(got, off, base, t.value, l.value)
+    # the split-row list (order of registration is free, content is not)
+    from oracle.partition_ref import split_rows
+    oc = L.b200spmv_csr_plan_ctl_offset(C.c_int64(rows), C.c_int64(nnz))
+    osp = L.b200spmv_csr_plan_split_offset(C.c_int64(rows), C.c_int64(nnz))
+    ctl = ws[oc:oc + 8].view(torch.int32).cpu().numpy()
+    nsplit = int(ctl[1])
+    assert ctl[0] == 0
+    lst = ws[osp:osp + 16 * nsplit].view(torch.int32).view(-1, 4).cpu().numpy()
+    assert sorted((int(a), int(b), int(c)) for a, b, c, _ in lst) == split_rows(want, off, base, t.value)
 
 
 def test_device_generators_are_bit_identical_to_the_oracle():
