@@ -7,6 +7,20 @@
 //   (cuSPARSE/spmv_sell/spmv_sell_example.c:103-122): column-major inside each slice, padding col = -1.
 #include "spmv_common.cuh"
 #include "../../include/b200spmv.h"
+#include <cstdlib>
+
+#ifndef B200_SELL_UNROLL
+#define B200_SELL_UNROLL 8
+#endif
+#ifndef B200_SELL_MIN_CTAS
+#define B200_SELL_MIN_CTAS 4
+#endif
+#ifndef B200_SELL32_MIN_CTAS
+#define B200_SELL32_MIN_CTAS 8   // 32 registers, 2048 threads/SM: measured 174 us vs 195 us at 40 registers (config 3)
+#endif
+#ifndef B200_SELL_WAVES      // persistent grid = SMs x resident CTAs x this
+#define B200_SELL_WAVES 1
+#endif
 
 namespace b200 {
 
@@ -135,12 +149,15 @@ static int launch_coo(cudaStream_t stream, int64_t rows, int64_t nnz, const void
 }
 
 // ================================================================================================
-// Sliced-ELL: one thread per row, slice-column-major storage makes the 32 lanes of a warp read 32
-// consecutive values / column indices for every k (fully coalesced when sliceSize is a multiple of
-// 32); the k loop is unrolled SELL_UNROLL deep so that many independent val/col/x loads are in flight.
+// Sliced-ELL: one thread per row; slice-column-major storage makes the 32 lanes of a warp read 32
+// consecutive values / column indices for every k (fully coalesced when sliceSize is a multiple of 32).
+// A thread's whole lifetime on one row would be three dependent memory round trips (slice offsets -> val/col
+// -> x) with nothing to overlap them, so the kernel is persistent and software-pipelined: every thread walks
+// rows r, r + stride, r + 2*stride, ... and the slice offsets and the first SELL_UNROLL val/col entries of the
+// NEXT row are already in flight into registers while the current row gathers x and accumulates.
 // ================================================================================================
 constexpr int SELL_BLOCK = 256;
-constexpr int SELL_UNROLL = 8;
+constexpr int SELL_UNROLL = B200_SELL_UNROLL;
 
 template <typename T>
 struct SellArgs {
@@ -156,34 +173,118 @@ struct SellArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(SELL_BLOCK) sell_row_kernel(const SellArgs<T> a) {
-    const int row = blockIdx.x * SELL_BLOCK + (int)threadIdx.x;
-    if (row >= a.rows) return;
-    const int C = a.slice_size;
+struct SellRow {
+    int    width;          // entries per row in this row's slice
+    size_t first;          // index of the row's k = 0 entry
+    int    c[SELL_UNROLL];
+    T      v[SELL_UNROLL];
+};
+
+// CS = compile-time slice size (0: use the run-time value).  With CS known the row -> slice division is a shift and
+// every val/col load of a row is `base pointer + immediate`, which matters: profiled on B200 the generic version is
+// bound by instruction issue (39 instructions per 32 non-zeros), not by memory.
+template <typename T, int CS>
+__device__ __forceinline__ void sell_issue(const SellArgs<T>& a, int row, SellRow<T>& r) {
+    const int C = CS ? CS : a.slice_size;
     const int s = row / C, lane = row - s * C;
     const int beg = __ldg(a.slice_off + s) - a.base, end = __ldg(a.slice_off + s + 1) - a.base;
-    const int width = (end - beg) / C;
+    r.width = (end - beg) / C;
+    r.first = (size_t)beg + lane;
+#pragma unroll
+    for (int u = 0; u < SELL_UNROLL; u++) {
+        const bool live = u < r.width;
+        r.c[u] = live ? ldg_stream(a.col + r.first + (size_t)u * C) - a.base : -1;
+        r.v[u] = live ? ldg_stream(a.val + r.first + (size_t)u * C) : T(0);
+    }
+}
+
+template <typename T, int CS>
+__global__ void __launch_bounds__(SELL_BLOCK, sizeof(T) == 4 ? B200_SELL_MIN_CTAS : (B200_SELL_MIN_CTAS > 3 ? 3 : B200_SELL_MIN_CTAS)) sell_row_kernel(const SellArgs<T> a) {
+    const int stride = (int)(gridDim.x * SELL_BLOCK);
+    int row = blockIdx.x * SELL_BLOCK + (int)threadIdx.x;
+    if (row >= a.rows) return;
+    const T alpha = a.s.a(), beta = a.s.b();
+    const int C = CS ? CS : a.slice_size;
+    SellRow<T> cur;
+    sell_issue<T, CS>(a, row, cur);
+    for (;;) {
+        const int  next = row + stride;
+        const bool has_next = next < a.rows;
+        SellRow<T> nxt;
+        T xx[SELL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SELL_UNROLL; u++) xx[u] = cur.c[u] >= 0 ? __ldg(a.x + cur.c[u]) : T(0);
+        if (has_next) sell_issue<T, CS>(a, next, nxt);   // next row's stream in flight before this row's gathers land
+        T sum = T(0);
+#pragma unroll
+        for (int u = 0; u < SELL_UNROLL; u++) sum += cur.v[u] * xx[u];
+        for (int k = SELL_UNROLL; k < cur.width; k += SELL_UNROLL) {      // slices wider than SELL_UNROLL
+            int cc[SELL_UNROLL];
+            T   vv[SELL_UNROLL], xv[SELL_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SELL_UNROLL; u++) {
+                const bool live = k + u < cur.width;
+                cc[u] = live ? ldg_stream(a.col + cur.first + (size_t)(k + u) * C) - a.base : -1;
+                vv[u] = live ? ldg_stream(a.val + cur.first + (size_t)(k + u) * C) : T(0);
+            }
+#pragma unroll
+            for (int u = 0; u < SELL_UNROLL; u++) xv[u] = cc[u] >= 0 ? __ldg(a.x + cc[u]) : T(0);
+#pragma unroll
+            for (int u = 0; u < SELL_UNROLL; u++) sum += vv[u] * xv[u];
+        }
+        T* yp = a.y + row;
+        *yp = axpby(alpha, sum, beta, yp);
+        if (!has_next) break;
+        row = next;
+        cur = nxt;
+    }
+}
+
+// Lean variant for sliceSize == 32 (one warp = one slice, so the slice width is warp-uniform): one thread per row, the
+// row's W entries are loaded with immediate offsets and no predicates (switch on W for W <= 8, fully unrolled), x is
+// gathered through a base pointer that already has the index base folded in.  ~10 instructions per non-zero instead
+// of ~20: this kernel is bound by instruction issue, not by memory, until it is this lean (profiles/).
+template <typename T, int W>
+__device__ __forceinline__ T sell32_row(const int* __restrict__ cp, const T* __restrict__ vp, const T* __restrict__ xp, int base) {
+    int c[W];
+    T   v[W], x[W];
+#pragma unroll
+    for (int u = 0; u < W; u++) { c[u] = ldg_stream(cp + u * 32); v[u] = ldg_stream(vp + u * 32); }
+#pragma unroll
+    for (int u = 0; u < W; u++) x[u] = c[u] >= base ? __ldg(xp + c[u]) : T(0);     // padding: column -1 (+base)
+    T sum = v[0] * x[0];
+#pragma unroll
+    for (int u = 1; u < W; u++) sum += v[u] * x[u];
+    return sum;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SELL_BLOCK, B200_SELL32_MIN_CTAS) sell32_kernel(const SellArgs<T> a) {
+    const int row = blockIdx.x * SELL_BLOCK + (int)threadIdx.x;
+    if (row >= a.rows) return;
+    const int s = row >> 5, lane = row & 31;
+    const int beg = __ldg(a.slice_off + s) - a.base, end = __ldg(a.slice_off + s + 1) - a.base;
+    const int width = (end - beg) >> 5;
     const int* cp = a.col + beg + lane;
     const T*   vp = a.val + beg + lane;
-    T sum = T(0);
-    int k = 0;
-    for (; k + SELL_UNROLL <= width; k += SELL_UNROLL) {
-        int cc[SELL_UNROLL];
-        T   vv[SELL_UNROLL], xx[SELL_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SELL_UNROLL; u++) {
-            cc[u] = ldg_stream(cp + (size_t)(k + u) * C) - a.base;
-            vv[u] = ldg_stream(vp + (size_t)(k + u) * C);
+    const T*   xp = a.x - a.base;
+    T sum;
+    switch (width) {                       // warp-uniform
+        case 0: sum = T(0); break;
+        case 1: sum = sell32_row<T, 1>(cp, vp, xp, a.base); break;
+        case 2: sum = sell32_row<T, 2>(cp, vp, xp, a.base); break;
+        case 3: sum = sell32_row<T, 3>(cp, vp, xp, a.base); break;
+        case 4: sum = sell32_row<T, 4>(cp, vp, xp, a.base); break;
+        case 5: sum = sell32_row<T, 5>(cp, vp, xp, a.base); break;
+        case 6: sum = sell32_row<T, 6>(cp, vp, xp, a.base); break;
+        case 7: sum = sell32_row<T, 7>(cp, vp, xp, a.base); break;
+        case 8: sum = sell32_row<T, 8>(cp, vp, xp, a.base); break;
+        default: {
+            sum = T(0);
+            int k = 0;
+            for (; k + 8 <= width; k += 8) sum += sell32_row<T, 8>(cp + k * 32, vp + k * 32, xp, a.base);
+            for (; k < width; k++) sum += sell32_row<T, 1>(cp + k * 32, vp + k * 32, xp, a.base);
         }
-#pragma unroll
-        for (int u = 0; u < SELL_UNROLL; u++) xx[u] = cc[u] >= 0 ? __ldg(a.x + cc[u]) : T(0);
-#pragma unroll
-        for (int u = 0; u < SELL_UNROLL; u++) sum += vv[u] * xx[u];
-    }
-    for (; k < width; k++) {
-        const int cc = ldg_stream(cp + (size_t)k * C) - a.base;
-        const T   vv = ldg_stream(vp + (size_t)k * C);
-        if (cc >= 0) sum += vv * __ldg(a.x + cc);
     }
     T* yp = a.y + row;
     *yp = axpby(a.s.a(), sum, a.s.b(), yp);
@@ -198,8 +299,25 @@ static int launch_sell(cudaStream_t stream, int64_t rows, int64_t slice_size, co
     a.base = base; a.rows = (int)rows; a.slice_size = (int)slice_size;
     if (on_device) { a.s.alpha = T(0); a.s.beta = T(0); a.s.alpha_dev = (const T*)alpha; a.s.beta_dev = (const T*)beta; }
     else { a.s.alpha = *(const T*)alpha; a.s.beta = *(const T*)beta; a.s.alpha_dev = nullptr; a.s.beta_dev = nullptr; }
-    const unsigned blocks = (unsigned)((rows + SELL_BLOCK - 1) / SELL_BLOCK);
-    sell_row_kernel<T><<<blocks, SELL_BLOCK, 0, stream>>>(a);
+    static int per_sm[2] = {0, 0};   // resident CTAs per SM, per value type
+    const int ti = sizeof(T) == 4 ? 0 : 1;
+    if (!per_sm[ti]) {
+        int n = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)sell_row_kernel<T, 0>, SELL_BLOCK, 0);
+        per_sm[ti] = n < 1 ? 1 : n;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t blocks = (rows + SELL_BLOCK - 1) / SELL_BLOCK;
+    const int64_t persistent = (int64_t)sms * per_sm[ti] * B200_SELL_WAVES;
+    if (blocks > persistent) blocks = persistent;
+    if (slice_size == 32 && !getenv("B200SPMV_SELL_GENERIC")) {
+        const int64_t all = (rows + SELL_BLOCK - 1) / SELL_BLOCK;
+        sell32_kernel<T><<<(unsigned)all, SELL_BLOCK, 0, stream>>>(a);
+    } else {
+        sell_row_kernel<T, 0><<<(unsigned)blocks, SELL_BLOCK, 0, stream>>>(a);
+    }
     return (int)cudaGetLastError();
 }
 

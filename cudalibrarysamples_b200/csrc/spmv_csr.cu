@@ -75,7 +75,7 @@ constexpr size_t PLAN_HEADER_BYTES = 256;
 
 struct PlanView {
     int2*   tiles;      // [num_tiles+1] (row, nnz) start coordinate of each tile
-    int*    ctl;        // [0] = CTAs that finished the current launch, [1] = number of split rows (set by analyze)
+    int*    ctl;        // [0] = arrivals of the current launch, [1] = number of split rows, [2] = number of partial sums (analyze)
     int4*   split;      // [num_tiles+1] split rows: (row, first covering tile b1, last covering tile b2, -)
     double* head_part;  // [num_tiles+1] partial sum of the split row a tile starts in
     double* tail_part;  // [num_tiles+1] partial sum of the split row a tile ends in
@@ -134,6 +134,7 @@ __global__ void csr_partition_kernel(const int* __restrict__ off, int base, int6
             if (b == b1 + 1) {
                 const int slot = atomicAdd(plan.ctl + 1, 1);
                 plan.split[slot] = make_int4((int)r, (int)b1, (int)b2, 0);
+                atomicAdd(plan.ctl + 2, (int)(b2 - b1 + 1));   // partial sums the covering tiles will deposit
             }
             n += e;
         }
@@ -292,9 +293,9 @@ __device__ __forceinline__ void split_rows_fixup(const CsrArgs<T>& a, T alpha, T
 // sP[0 .. ne-ns) holds the tile's products, sOff[i] - shift = rowOff[rs+i] - base - ns for i = 0 .. re-rs (the
 // tile / pipe kernels stage rebased offsets, shift = 0; the TMA-fed kernel stages the raw slice, shift = base + ns).
 template <typename T, typename OT, int BLOCK, int BAR_ID>
-__device__ __forceinline__ void tile_phase2(const CsrArgs<T>& a, int b, int rs, int ns, int re, int ne, const T* sP,
-                                            const OT* sOff, int shift, T* sRed, T alpha, T beta, int tid) {
-    if (B200_CSR_ABLATE & 1) { if (sP[tid] == T(1.2345)) a.y[0] = sP[0]; return; }
+__device__ __forceinline__ int tile_phase2(const CsrArgs<T>& a, int b, int rs, int ns, int re, int ne, const T* sP,
+                                           const OT* sOff, int shift, T* sRed, T alpha, T beta, int tid) {
+    if (B200_CSR_ABLATE & 1) { if (sP[tid] == T(1.2345)) a.y[0] = sP[0]; return 0; }
     const int cnt = ne - ns;
     bool head = false;
     int  head_end = 0;  // products [0, head_end) belong to the split row rs
@@ -331,6 +332,33 @@ __device__ __forceinline__ void tile_phase2(const CsrArgs<T>& a, int b, int rs, 
         const T ts = block_sum_range<T, BLOCK, BAR_ID>(sP, tail_beg, cnt, sRed, tid);
         if (tid == 0) a.plan.tail_part[b] = (double)ts;
     }
+    return (head ? 1 : 0) + (tail ? 1 : 0);   // partial sums this tile deposited (group-uniform)
+}
+
+// One-CTA-per-tile kernels: only the CTAs that deposited partial sums take part in the arrival count (its target,
+// ctl[2], is known from analyze); the one that completes it adds up all split rows.  Those CTAs sit where the long
+// rows are, so the fix-up runs in the shadow of the remaining tiles.  `npart` must be block-uniform.
+template <typename T>
+__device__ __forceinline__ void split_rows_fixup_by_depositors(const CsrArgs<T>& a, int npart, T alpha, T beta) {
+    if (npart == 0) return;
+    __shared__ int s_last2;
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // my partial sums first
+        const int old = atomicAdd(a.plan.ctl, npart);
+        s_last2 = (old + npart == __ldcg(a.plan.ctl + 2));
+    }
+    __syncthreads();
+    if (!s_last2) return;
+    __threadfence();
+    const int nsplit = __ldcg(a.plan.ctl + 1);
+    for (int i = (int)threadIdx.x; i < nsplit; i += (int)blockDim.x) {
+        const int4 sr = a.plan.split[i];
+        double sum = __ldcg(a.plan.tail_part + sr.y);
+        for (int b = sr.y + 1; b <= sr.z; b++) sum += __ldcg(a.plan.head_part + b);
+        T* yp = a.y + sr.x;
+        *yp = axpby(alpha, (T)sum, beta, yp);
+    }
+    if (threadIdx.x == 0) a.plan.ctl[0] = 0;
 }
 
 template <typename T>
@@ -391,24 +419,11 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
     __syncthreads();
     TRACE_STAMP(a, b, 1);
 
-    tile_phase2<T, int, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
+    const int npart = tile_phase2<T, int, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
     TRACE_STAMP(a, b, 2);
+    split_rows_fixup_by_depositors<T>(a, npart, alpha, beta);
 }
 
-// One-CTA-per-tile launches cannot afford an exit protocol in every CTA: their split rows are combined by this
-// small second launch instead (same arithmetic, same fixed order as split_rows_fixup).
-template <typename T>
-__global__ void __launch_bounds__(256) csr_fixup_kernel(const CsrArgs<T> a) {
-    const T alpha = a.s.a(), beta = a.s.b();
-    const int nsplit = a.plan.ctl[1];
-    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < nsplit; i += (int)(gridDim.x * blockDim.x)) {
-        const int4 sr = a.plan.split[i];
-        double sum = __ldcg(a.plan.tail_part + sr.y);
-        for (int b = sr.y + 1; b <= sr.z; b++) sum += __ldcg(a.plan.head_part + b);
-        T* yp = a.y + sr.x;
-        *yp = axpby(alpha, (T)sum, beta, yp);
-    }
-}
 
 // ================================================================================================
 // Persistent, software-pipelined variant (the default): each CTA walks tiles b, b+grid, b+2*grid, ...
@@ -876,6 +891,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_RW_MIN_CTAS) csr_rowwise_kerne
         const T ts = block_dot_range<T, CSR_BLOCK>(a, tail_beg, ne, sRed, tid);
         if (tid == 0) a.plan.tail_part[b] = (double)ts;
     }
+    split_rows_fixup_by_depositors<T>(a, (head ? 1 : 0) + (tail ? 1 : 0), alpha, beta);
 }
 
 // SMs x resident CTAs per SM of a kernel on the current device (cached per device / kernel).
@@ -925,10 +941,8 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
     if (mode == 2 && (((uintptr_t)col | (uintptr_t)val | (uintptr_t)off) & 15) != 0) mode = 1;   // TMA needs 16 B alignment
     if (mode == 0) {
         csr_tile_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
-        csr_fixup_kernel<T><<<8, 256, 0, stream>>>(a);
     } else if (mode == 3) {
         csr_rowwise_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
-        csr_fixup_kernel<T><<<8, 256, 0, stream>>>(a);
     } else if (mode == 2) {
         const size_t dyn = (size_t)WS_STAGES * WsStage<T>::bytes;
         int64_t grid = (int64_t)resident_ctas((const void*)csr_ws_kernel<T>, WS_THREADS, dyn);

@@ -134,11 +134,17 @@ def test_solver_samples_reproduce_the_readme_trace(name, iters):
 
 
 # ---------------------------------------------------------------------------- oracle + closed library
+_RMAT_CACHE = {}
+
+
 def rmat_case(rows, avg, dtype, seed):
-    off, col, val = O.rmat_csr(rows, avg_nnz=avg, seed=seed, val_seed=seed + 1, dtype=NP[dtype])
-    x = O.uniform(seed + 2, rows, NP[dtype])
-    y0 = O.uniform(seed + 3, rows, NP[dtype])
-    return off, col, val, x, y0
+    key = (rows, avg, dtype, seed)
+    if key not in _RMAT_CACHE:
+        off, col, val = O.rmat_csr(rows, avg_nnz=avg, seed=seed, val_seed=seed + 1, dtype=NP[dtype])
+        x = O.uniform(seed + 2, rows, NP[dtype])
+        y0 = O.uniform(seed + 3, rows, NP[dtype])
+        _RMAT_CACHE[key] = (off, col, val, x, y0)
+    return _RMAT_CACHE[key]
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
@@ -243,11 +249,32 @@ def test_every_csr_kernel_variant_edge_profiles(cs, b200, csr_kernel, name):
     assert relerr(got, want) < 1e-12, (csr_kernel, name)
 
 
+_CSR_CACHE = {}
+
+
 def lens_to_csr(lens, cols, seed, dtype=np.float64):
+    """Random CSR with the given row lengths (distinct sorted columns per row); cached: several tests share profiles."""
+    key = (lens.tobytes(), cols, seed, np.dtype(dtype).str)
+    if key in _CSR_CACHE:
+        return _CSR_CACHE[key]
     rng = np.random.default_rng(seed)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-    col = np.concatenate([np.sort(rng.choice(cols, size=l, replace=False)) for l in lens] + [np.zeros(0, int)]).astype(np.int32)
+    parts = []
+    for l in lens:
+        l = int(l)
+        if l == 0:
+            continue
+        if l > cols // 8:
+            c = rng.choice(cols, size=l, replace=False)
+        else:                       # cheap rejection sampling for short rows
+            c = np.unique(rng.integers(0, cols, size=2 * l + 8))
+            while c.size < l:
+                c = np.unique(np.concatenate([c, rng.integers(0, cols, size=2 * l + 8)]))
+            c = rng.permutation(c)[:l]
+        parts.append(np.sort(c))
+    col = (np.concatenate(parts) if parts else np.zeros(0, int)).astype(np.int32)
     val = rng.uniform(-1, 1, off[-1]).astype(dtype)
+    _CSR_CACHE[key] = (off, col, val)
     return off, col, val
 
 
