@@ -159,7 +159,7 @@ def workload_config(n_gpus, rows, nnz):
                     "(a,b,c,d)=(0.57,0.19,0.19,0.05), seed 42, duplicates merged, columns sorted, val,x~U(-1,1), int32 indices",
         "baseline_config": "BASELINE.json configs[1] (R-MAT 1M x 1M avg 16 nnz/row, single B200); N>1 grows the matrix to N*1M rows",
         "rows": rows, "cols": rows, "nnz": nnz, "alpha": 1.0, "beta": 0.0,
-        "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} row-block shards (nnz-balanced), one NCCL all-gather of x per step",
+        "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} row-block shards of A and y (nnz-balanced), x in equal blocks, one NCCL all-gather of x per step",
         "l2": "no flush: 212 MB streamed per step per GPU > 126 MB L2; x stays L2-resident by design",
     }
 
@@ -227,6 +227,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dist_on = world > 1
     if dist_on:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; the contract is ONE JSON line on stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -238,7 +241,7 @@ def run_ours(args):
     nnz = int(col.numel())
     x = W.uniform(44, rows)
     total_bytes = csr_bytes(rows, rows, nnz)
-    launches_per_step = 1
+    launches_per_step = 2 if nnz >= 12 * rows else 1   # csr_tile_kernel + csr_fixup_kernel, or the single persistent csr_pipe_kernel
 
     if not dist_on:
         op = cs.SpMVOperator(api, "csr", rows, rows, dict(off=off, col=col, val=val), preprocess=True)
@@ -254,16 +257,30 @@ def run_ours(args):
         sh = ShardedCsr(off, col, val, rank, world, make_local)
         del off, col, val
         torch.cuda.empty_cache()
-        xs = sh.new_shard(x)
-        ys = sh.new_shard()
+        xs = sh.new_x_shard(x)
+        ys = sh.new_y_shard()
         lop = make_local.op
-        local_call = prebuilt_spmv_call(cs, lop, sh.x_full, ys[:sh.rows])
+        local_call = prebuilt_spmv_call(cs, lop, sh.x_full, ys)
 
         def step():
             dist.all_gather_into_tensor(sh.x_full, xs)
             local_call()
         kernel_bytes = csr_bytes(sh.rows, sh.cols_padded, sh.nnz)
-        local = dict(rows=sh.rows, nnz=sh.nnz, pad=sh.pad)
+        local = dict(rows=sh.rows, nnz=sh.nnz, x_block=sh.x_block)
+        # parity of the sharded product at full size: every rank checks its y shard against the closed library run
+        # on the same local arrays and the gathered x (max relative difference over ranks goes into the JSON line)
+        step()
+        torch.cuda.synchronize()
+        capi = cs.Api("cusparse")
+        cop = cs.SpMVOperator(capi, "csr", sh.rows, sh.cols_padded, dict(off=sh.off, col=sh.col, val=sh.val), preprocess=True)
+        yc = torch.zeros_like(ys)
+        cop(sh.x_full, yc, 1.0, 0.0)
+        torch.cuda.synchronize()
+        shard_rel = (torch.linalg.norm(ys - yc) / torch.linalg.norm(yc)).reshape(1)
+        dist.all_reduce(shard_rel, op=dist.ReduceOp.MAX)
+        local["max_rel_diff_vs_cusparse_over_ranks"] = float(shard_rel.item())
+        assert local["max_rel_diff_vs_cusparse_over_ranks"] < 1e-12
+        cop.close()
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -314,7 +331,7 @@ def run_ours(args):
         assert torch.equal(hy, y.cpu()), "e2e result differs from the device-resident result"
     else:
         hx = xs.cpu().pin_memory()
-        hy = torch.empty(sh.pad, dtype=torch.float64).pin_memory()
+        hy = torch.empty(max(sh.rows, 1), dtype=torch.float64).pin_memory()[:sh.rows]
 
         def e2e_step():
             xs.copy_(hx, non_blocking=True)
@@ -324,7 +341,7 @@ def run_ours(args):
             e2e_step()
         ms_e, _, _ = time_steps(torch, e2e_step, args.steps, True)
         e2e = {"value": round(total_bytes / (ms_e / args.steps * 1e-3) / 1e9, 3), "unit": UNIT,
-               "h2d_bytes_per_step": sh.pad * 8 * world, "d2h_bytes_per_step": sh.pad * 8 * world,
+               "h2d_bytes_per_step": sh.x_block * 8 * world, "d2h_bytes_per_step": rows * 8,
                "ms_per_step": round(ms_e / args.steps, 4),
                "what": "per rank: pinned host x shard -> device, all-gather + cusparseSpMV, device y shard -> pinned host"}
 

@@ -56,6 +56,9 @@ namespace b200 {
 #ifndef B200_CSR_RED_ROWS     // rows a lane group reduces concurrently in phase 2
 #define B200_CSR_RED_ROWS 2
 #endif
+#ifndef B200_CSR_RED_BUTTERFLY
+#define B200_CSR_RED_BUTTERFLY 1
+#endif
 #ifndef B200_CSR_RED_U        // predicated product loads per lane and row before the fall-back loop
 #define B200_CSR_RED_U 2
 #endif
@@ -202,6 +205,7 @@ __device__ __forceinline__ T block_sum_range(const T* sP, int lo, int hi, T* sRe
 // a group of G lanes therefore works on ROWS rows at once -- all row bounds first, then all products (U predicated
 // loads per lane and row, enough for rows up to U*G long), then ROWS interleaved shuffle trees.
 constexpr int RED_ROWS = B200_CSR_RED_ROWS;
+constexpr int RED_ROWS4 = B200_CSR_RED_BUTTERFLY ? 4 : B200_CSR_RED_ROWS;   // groups of >= 4 lanes: 4 rows + transposed butterfly
 constexpr int RED_U    = B200_CSR_RED_U;
 
 template <typename T, typename OT, int G, int ROWS, int U, int BLOCK>
@@ -244,18 +248,73 @@ __device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, co
                 for (int u = 0; u < U; u++) sum[i] += q[u];
             }
         }
+        if (ROWS == 4 && G >= 4) {
+            // Transposed butterfly: 4 row sums over G lanes in 2 + 1 + log2(G/4) exchanges instead of 4*log2(G)
+            // (shuffles queue in the same L1TEX pipe as the gathers).  After the first two exchanges every lane of
+            // quarter q = 2*hi + mid of the group carries one partial of row slot q.
+            const bool hi = (gl & (G / 2)) != 0, mid = (gl & (G / 4)) != 0;
+            const T s0 = hi ? sum[0] : sum[2], s1 = hi ? sum[1] : sum[3];
+            T k0v = (hi ? sum[2] : sum[0]) + __shfl_xor_sync(0xffffffffu, s0, G / 2);
+            T k1v = (hi ? sum[3] : sum[1]) + __shfl_xor_sync(0xffffffffu, s1, G / 2);
+            T kv  = (mid ? k1v : k0v) + __shfl_xor_sync(0xffffffffu, mid ? k0v : k1v, G / 4);
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1)
-#pragma unroll
-            for (int i = 0; i < ROWS; i++) sum[i] += __shfl_down_sync(0xffffffffu, sum[i], o, G);
-        if (gl == 0) {
-#pragma unroll
-            for (int i = 0; i < ROWS; i++) {
-                const int ri = r0 + i * GROUPS + gid;
+            for (int o = G / 8; o > 0; o >>= 1) kv += __shfl_xor_sync(0xffffffffu, kv, o);
+            if ((gl & (G / 4 - 1)) == 0) {
+                const int slot = (hi ? 2 : 0) + (mid ? 1 : 0);
+                const int ri = r0 + slot * GROUPS + gid;
                 if (ri < nrows) {
                     T* yp = a.y + r_first + ri;
-                    *yp = axpby(alpha, sum[i], beta, yp);
+                    *yp = axpby(alpha, kv, beta, yp);
                 }
+            }
+        } else {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+                for (int i = 0; i < ROWS; i++) sum[i] += __shfl_down_sync(0xffffffffu, sum[i], o, G);
+            if (gl == 0) {
+#pragma unroll
+                for (int i = 0; i < ROWS; i++) {
+                    const int ri = r0 + i * GROUPS + gid;
+                    if (ri < nrows) {
+                        T* yp = a.y + r_first + ri;
+                        *yp = axpby(alpha, sum[i], beta, yp);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// y[R] = alpha * (tail_part[b1] + head_part[b1+1] + ... + head_part[b2]) + beta * y[R] for every split row, by one
+// CTA (or, from the fix-up kernel, by the whole grid), in fixed tile order (bit-reproducible).  Four rows per thread are in flight at a time: the loads of one row are
+// a dependent chain of L2 round trips, and a 10 M-row R-MAT has ~10^5 partial sums to add.
+template <typename T>
+__device__ __forceinline__ void sum_split_rows(const CsrArgs<T>& a, T alpha, T beta, bool whole_grid = false) {
+    constexpr int RU = 4;
+    const int nsplit = __ldcg(a.plan.ctl + 1);
+    const int nthr = (int)blockDim.x * (whole_grid ? (int)gridDim.x : 1);
+    for (int i0 = (int)threadIdx.x + (whole_grid ? (int)(blockIdx.x * blockDim.x) : 0); i0 < nsplit; i0 += RU * nthr) {
+        int4   sr[RU];
+        double sum[RU], h1[RU];
+#pragma unroll
+        for (int j = 0; j < RU; j++) {
+            const int i = i0 + j * nthr;
+            sr[j] = i < nsplit ? a.plan.split[i] : make_int4(-1, 0, -1, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < RU; j++) {
+            const bool live = sr[j].x >= 0;
+            sum[j] = live ? __ldcg(a.plan.tail_part + sr[j].y) : 0.0;
+            h1[j]  = (live && sr[j].z > sr[j].y) ? __ldcg(a.plan.head_part + sr[j].y + 1) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < RU; j++) {
+            sum[j] += h1[j];
+            for (int b = sr[j].y + 2; b <= sr[j].z; b++) sum[j] += __ldcg(a.plan.head_part + b);   // rows cut more than once
+            if (sr[j].x >= 0) {
+                T* yp = a.y + sr[j].x;
+                *yp = axpby(alpha, (T)sum[j], beta, yp);
             }
         }
     }
@@ -278,14 +337,7 @@ __device__ __forceinline__ void split_rows_fixup(const CsrArgs<T>& a, T alpha, T
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int nsplit = __ldcg(a.plan.ctl + 1);
-    for (int i = (int)threadIdx.x; i < nsplit; i += (int)blockDim.x) {
-        const int4 sr = a.plan.split[i];
-        double sum = __ldcg(a.plan.tail_part + sr.y);
-        for (int b = sr.y + 1; b <= sr.z; b++) sum += __ldcg(a.plan.head_part + b);
-        T* yp = a.y + sr.x;
-        *yp = axpby(alpha, (T)sum, beta, yp);
-    }
+    sum_split_rows<T>(a, alpha, beta);
     if (threadIdx.x == 0) a.plan.ctl[0] = 0;
 }
 
@@ -318,9 +370,9 @@ __device__ __forceinline__ int tile_phase2(const CsrArgs<T>& a, int b, int rs, i
         const int avg2 = body / (2 * nrows);  // half the mean row length
         if      (avg2 <= 1)  reduce_rows<T, OT, 1, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
         else if (avg2 <= 2)  reduce_rows<T, OT, 2, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 4)  reduce_rows<T, OT, 4, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 8)  reduce_rows<T, OT, 8, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 16) reduce_rows<T, OT, 16, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 4)  reduce_rows<T, OT, 4, RED_ROWS4, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 8)  reduce_rows<T, OT, 8, RED_ROWS4, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 16) reduce_rows<T, OT, 16, RED_ROWS4, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
         else                 reduce_rows<T, OT, 32, 2, 8, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);  // long rows: 256 elements per batch
     }
 
@@ -335,31 +387,6 @@ __device__ __forceinline__ int tile_phase2(const CsrArgs<T>& a, int b, int rs, i
     return (head ? 1 : 0) + (tail ? 1 : 0);   // partial sums this tile deposited (group-uniform)
 }
 
-// One-CTA-per-tile kernels: only the CTAs that deposited partial sums take part in the arrival count (its target,
-// ctl[2], is known from analyze); the one that completes it adds up all split rows.  Those CTAs sit where the long
-// rows are, so the fix-up runs in the shadow of the remaining tiles.  `npart` must be block-uniform.
-template <typename T>
-__device__ __forceinline__ void split_rows_fixup_by_depositors(const CsrArgs<T>& a, int npart, T alpha, T beta) {
-    if (npart == 0) return;
-    __shared__ int s_last2;
-    if (threadIdx.x == 0) {
-        __threadfence();                                   // my partial sums first
-        const int old = atomicAdd(a.plan.ctl, npart);
-        s_last2 = (old + npart == __ldcg(a.plan.ctl + 2));
-    }
-    __syncthreads();
-    if (!s_last2) return;
-    __threadfence();
-    const int nsplit = __ldcg(a.plan.ctl + 1);
-    for (int i = (int)threadIdx.x; i < nsplit; i += (int)blockDim.x) {
-        const int4 sr = a.plan.split[i];
-        double sum = __ldcg(a.plan.tail_part + sr.y);
-        for (int b = sr.y + 1; b <= sr.z; b++) sum += __ldcg(a.plan.head_part + b);
-        T* yp = a.y + sr.x;
-        *yp = axpby(alpha, (T)sum, beta, yp);
-    }
-    if (threadIdx.x == 0) a.plan.ctl[0] = 0;
-}
 
 template <typename T>
 __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel(const CsrArgs<T> a) {
@@ -372,6 +399,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
     const int  rs = st.x, ns = st.y, re = en.x, ne = en.y;
     const T alpha = a.s.a(), beta = a.s.b();
     TRACE_STAMP(a, b, 0); TRACE_SMID(a, b);
+    cudaTriggerProgrammaticLaunchCompletion();   // lets csr_fixup_kernel get resident early (it still waits for our completion)
 
     // ---------------- phase 1: stream val/col, gather x, park products in shared memory -------------
     // Lane l of a warp handles element (step*BLOCK + warp*32 + l): every load/gather instruction covers 32
@@ -419,9 +447,38 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
     __syncthreads();
     TRACE_STAMP(a, b, 1);
 
-    const int npart = tile_phase2<T, int, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
+    tile_phase2<T, int, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
     TRACE_STAMP(a, b, 2);
-    split_rows_fixup_by_depositors<T>(a, npart, alpha, beta);
+}
+
+// One-CTA-per-tile launches leave the split rows to this small second launch.  (Measured alternatives: an arrival
+// counter bumped by every CTA, or only by the CTAs that deposited partial sums, costs 5-25 % on R-MAT because a whole
+// CTA waits for one atomic round trip; the extra launch costs ~4 us.)
+template <typename T>
+__global__ void __launch_bounds__(256) csr_fixup_kernel(const CsrArgs<T> a) {
+    // Launched with programmatic stream serialization: these 16 CTAs may become resident while the tile kernel is
+    // still running (it triggers early), so the launch latency is hidden; they wait here until the tile kernel's
+    // memory is complete and visible.
+    cudaGridDependencySynchronize();
+    sum_split_rows<T>(a, a.s.a(), a.s.b(), /*whole_grid=*/true);
+}
+
+template <typename T>
+static void launch_fixup(const CsrArgs<T>& a, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, csr_fixup_kernel<T>, a) != cudaSuccess) {
+        (void)cudaGetLastError();
+        csr_fixup_kernel<T><<<16, 256, 0, stream>>>(a);      // plain stream order is always correct
+    }
 }
 
 
@@ -805,17 +862,38 @@ __device__ __forceinline__ void rowwise_rows(const CsrArgs<T>& a, int r_first, i
                 for (int u = 0; u < U; u++) sum[i] += vv[u] * xx[u];
             }
         }
+        if (ROWS == 4 && G >= 4) {
+            // Transposed butterfly: 4 row sums over G lanes in 2 + 1 + log2(G/4) exchanges instead of 4*log2(G)
+            // (shuffles queue in the same L1TEX pipe as the gathers).  After the first two exchanges every lane of
+            // quarter q = 2*hi + mid of the group carries one partial of row slot q.
+            const bool hi = (gl & (G / 2)) != 0, mid = (gl & (G / 4)) != 0;
+            const T s0 = hi ? sum[0] : sum[2], s1 = hi ? sum[1] : sum[3];
+            T k0v = (hi ? sum[2] : sum[0]) + __shfl_xor_sync(0xffffffffu, s0, G / 2);
+            T k1v = (hi ? sum[3] : sum[1]) + __shfl_xor_sync(0xffffffffu, s1, G / 2);
+            T kv  = (mid ? k1v : k0v) + __shfl_xor_sync(0xffffffffu, mid ? k0v : k1v, G / 4);
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1)
-#pragma unroll
-            for (int i = 0; i < ROWS; i++) sum[i] += __shfl_down_sync(0xffffffffu, sum[i], o, G);
-        if (gl == 0) {
-#pragma unroll
-            for (int i = 0; i < ROWS; i++) {
-                const int ri = r0 + i * GROUPS + gid;
+            for (int o = G / 8; o > 0; o >>= 1) kv += __shfl_xor_sync(0xffffffffu, kv, o);
+            if ((gl & (G / 4 - 1)) == 0) {
+                const int slot = (hi ? 2 : 0) + (mid ? 1 : 0);
+                const int ri = r0 + slot * GROUPS + gid;
                 if (ri < nrows) {
                     T* yp = a.y + r_first + ri;
-                    *yp = axpby(alpha, sum[i], beta, yp);
+                    *yp = axpby(alpha, kv, beta, yp);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+                for (int i = 0; i < ROWS; i++) sum[i] += __shfl_down_sync(0xffffffffu, sum[i], o, G);
+            if (gl == 0) {
+#pragma unroll
+                for (int i = 0; i < ROWS; i++) {
+                    const int ri = r0 + i * GROUPS + gid;
+                    if (ri < nrows) {
+                        T* yp = a.y + r_first + ri;
+                        *yp = axpby(alpha, sum[i], beta, yp);
+                    }
                 }
             }
         }
@@ -857,6 +935,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_RW_MIN_CTAS) csr_rowwise_kerne
     const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
     const int  rs = st.x, ns = st.y, re = en.x, ne = en.y;
     const T alpha = a.s.a(), beta = a.s.b();
+    cudaTriggerProgrammaticLaunchCompletion();
 
     bool head = false;
     int  head_end = ns;                      // non-zeros [ns, head_end) belong to the split row rs
@@ -891,7 +970,6 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_RW_MIN_CTAS) csr_rowwise_kerne
         const T ts = block_dot_range<T, CSR_BLOCK>(a, tail_beg, ne, sRed, tid);
         if (tid == 0) a.plan.tail_part[b] = (double)ts;
     }
-    split_rows_fixup_by_depositors<T>(a, (head ? 1 : 0) + (tail ? 1 : 0), alpha, beta);
 }
 
 // SMs x resident CTAs per SM of a kernel on the current device (cached per device / kernel).
@@ -941,8 +1019,10 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
     if (mode == 2 && (((uintptr_t)col | (uintptr_t)val | (uintptr_t)off) & 15) != 0) mode = 1;   // TMA needs 16 B alignment
     if (mode == 0) {
         csr_tile_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+        launch_fixup<T>(a, stream);
     } else if (mode == 3) {
         csr_rowwise_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+        launch_fixup<T>(a, stream);
     } else if (mode == 2) {
         const size_t dyn = (size_t)WS_STAGES * WsStage<T>::bytes;
         int64_t grid = (int64_t)resident_ctas((const void*)csr_ws_kernel<T>, WS_THREADS, dyn);

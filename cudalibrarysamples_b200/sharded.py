@@ -5,10 +5,9 @@ rank holds ~nnz/G non-zeros, not rows/G, because R-MAT rows are skewed -- plus t
 exchange step of the path is one all-gather of x (NCCL over NVLink 5 / NVSwitch) right before the local kernel; in CG the x
 shard of one product is the y shard of the previous one, so the gather sits on the critical path of every iteration.
 
-Shards have different row counts, so the gathered vector uses a padded layout: shard g occupies
-x_full[g*pad : g*pad + rows_g], pad = max_g rows_g, and the local column indices are remapped into that layout ONCE at
-set-up (structure-only preprocessing, like the tile plan).  The local product is then an ordinary rows_g x (G*pad) CSR SpMV
-through the same C ABI as the single-GPU path.
+x itself is distributed in EQUAL blocks (not by the row blocks), so the gather moves exactly |x|*(G-1)/G bytes per
+rank, no padding, and the gathered buffer is x: the local product is an ordinary rows_g x cols CSR SpMV through the
+same C ABI as the single-GPU path, on the caller's unmodified column indices.
 
 Host logic only -- the local kernel is injected (`make_local_op`) so the world_size-2 gloo tests on CPU can drive the
 same code with the CPU oracle, while bench.py passes the sm_100a operator.
@@ -34,54 +33,71 @@ def split_rows_by_nnz(off: torch.Tensor, world: int) -> torch.Tensor:
 
 
 class ShardedCsr:
-    """This rank's row block of a global square CSR matrix plus the padded all-gather layout for x."""
+    """This rank's row block of a global square CSR matrix plus the all-gather layout for x.
+
+    Two distributions, both fixed at set-up:
+      * A and y by contiguous row blocks with ~nnz/G non-zeros each (rows [r0, r1) on this rank);
+      * x by EQUAL blocks of x_block = ceil(n/G) entries (the last one zero-padded), so the exchange step is one
+        all_gather_into_tensor of equal shards with no padding traffic, and the gathered vector is x itself:
+        column indices need no remapping.
+    (In a solver loop y becomes the next x: with skewed matrices the two distributions differ and the hand-over is a
+    redistribution of the row-block / equal-block overlap; for banded matrices they coincide up to a halo.)
+    """
 
     def __init__(self, off: torch.Tensor, col: torch.Tensor, val: torch.Tensor, rank: int, world: int,
-                 make_local_op: Callable[[int, int, dict], Callable], group=None, base: int = 0):
+                 make_local_op: Callable[[int, int, dict], Callable], group=None, base: int = 0, balance: str = "nnz"):
         assert base == 0
         self.rank, self.world, self.group = rank, world, group
         n = off.numel() - 1
         self.global_rows = n
         self.global_nnz = int(off[-1].item())
-        self.bounds = split_rows_by_nnz(off, world)               # [world+1], identical on every rank
+        if balance == "nnz":
+            self.bounds = split_rows_by_nnz(off, world)           # [world+1], identical on every rank
+        else:   # "rows": equal row blocks == the x blocks (regular matrices; lets a solver hand y over as the next x)
+            blk = max(1, (n + world - 1) // world)
+            self.bounds = torch.tensor([min(g * blk, n) for g in range(world + 1)], dtype=torch.int64, device=off.device)
         b = self.bounds.tolist()
         self.r0, self.r1 = b[rank], b[rank + 1]
         self.rows = self.r1 - self.r0
-        self.pad = max(1, max(b[g + 1] - b[g] for g in range(world)))
+        self.x_block = max(1, (n + world - 1) // world)
+        self.pad = self.x_block                                    # length of one x shard
         n0, n1 = int(off[self.r0].item()), int(off[self.r1].item())
         self.off = (off[self.r0:self.r1 + 1].to(torch.int64) - n0).to(torch.int32).contiguous()
-        gcol = col[n0:n1].to(torch.int64)
-        owner = torch.searchsorted(self.bounds[1:].contiguous(), gcol, right=True)          # block that owns the column
-        self.col = (owner * self.pad + (gcol - self.bounds[owner])).to(torch.int32).contiguous()
+        self.col = col[n0:n1].contiguous()
         self.val = val[n0:n1].contiguous()
         self.nnz = n1 - n0
-        self.cols_padded = world * self.pad
+        self.cols_padded = world * self.x_block
         self.x_full = torch.zeros(self.cols_padded, dtype=val.dtype, device=val.device)
         self.local_op = make_local_op(self.rows, self.cols_padded, dict(off=self.off, col=self.col, val=self.val))
 
-    def new_shard(self, fill=None):
-        """A padded vector shard (pad entries, the first `rows` are live)."""
-        t = torch.zeros(self.pad, dtype=self.val.dtype, device=self.val.device)
-        if fill is not None:
-            t[:self.rows] = fill[self.r0:self.r1]
+    def new_x_shard(self, x=None):
+        """This rank's equal block of a global vector x (zero-padded at the end of the last block)."""
+        t = torch.zeros(self.x_block, dtype=self.val.dtype, device=self.val.device)
+        if x is not None:
+            lo = self.rank * self.x_block
+            hi = min(lo + self.x_block, self.global_rows)
+            if hi > lo:
+                t[:hi - lo] = x[lo:hi]
+        return t
+
+    def new_y_shard(self, y=None):
+        """This rank's row block of a global vector y."""
+        t = torch.zeros(max(self.rows, 1), dtype=self.val.dtype, device=self.val.device)[:self.rows]
+        if y is not None and self.rows:
+            t.copy_(y[self.r0:self.r1])
         return t
 
     def gather_x(self, x_shard: torch.Tensor) -> torch.Tensor:
-        """The path's single exchange step: all-gather of the padded x shards."""
+        """The path's single exchange step: all-gather of the equal x shards."""
         if self.world == 1:
-            self.x_full[:self.pad].copy_(x_shard)
+            self.x_full[:self.x_block].copy_(x_shard)
         else:
             dist.all_gather_into_tensor(self.x_full, x_shard, group=self.group)
         return self.x_full
 
     def spmv(self, x_shard: torch.Tensor, y_shard: torch.Tensor, alpha=1.0, beta=0.0) -> torch.Tensor:
-        """y_shard[:rows] = alpha * A[r0:r1, :] @ x + beta * y_shard[:rows]   (x given as this rank's padded shard)."""
+        """y_shard = alpha * A[r0:r1, :] @ x + beta * y_shard   (x given as this rank's equal block)."""
         self.gather_x(x_shard)
         if self.rows > 0:
-            self.local_op(self.x_full, y_shard[:self.rows], alpha, beta)
+            self.local_op(self.x_full, y_shard, alpha, beta)
         return y_shard
-
-    def unpad(self, x_full: torch.Tensor) -> torch.Tensor:
-        """Padded gathered layout -> the global vector (test helper)."""
-        b = self.bounds.tolist()
-        return torch.cat([x_full[g * self.pad: g * self.pad + (b[g + 1] - b[g])] for g in range(self.world)])

@@ -81,6 +81,8 @@ if os.environ.get("SWEEP_SET") == "final":
         "pipe_occ4": dict(TILE=2048, LONG=512, BLOCK=256, BATCH=4, MIN=4, KERNEL=1, OFFS=4, RR=2, RU=4),
         "rw_b128_occ8": dict(TILE=2048, LONG=512, BLOCK=128, BATCH=4, MIN=8, KERNEL=3, RW=(4, 2)),
     }
+if os.environ.get("SWEEP_SET") == "ab":
+    VARIANTS = {"nobfly": {}, "nobfly_r4": {}, "bfly_occ6": {}, "nobfly_occ6": {}}
 if os.environ.get("SWEEP_SET") == "ablate":
     VARIANTS = dict(ABL, t2048_b256_k4_occ6=VARIANTS["t2048_b256_k4_occ6"])
 

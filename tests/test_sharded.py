@@ -36,16 +36,19 @@ def _worker(rank, world, port, rows, q):
         x = torch.from_numpy(O.uniform(5, rows))
         y0 = torch.from_numpy(O.uniform(6, rows))
         sh = ShardedCsr(off, col, val, rank, world, _oracle_op)
-        xs, ys = sh.new_shard(x), sh.new_shard(y0)
+        xs, ys = sh.new_x_shard(x), sh.new_y_shard(y0)
         sh.spmv(xs, ys, alpha=-1.0, beta=1.0)
-        # second product chained on the first (CG style: y shard becomes the next x shard)
-        zs = sh.new_shard()
-        sh.spmv(ys, zs, alpha=1.0, beta=0.0)
-        # per-rank non-zero balance and the reassembled x
-        gathered = sh.unpad(sh.x_full)
+        # second product chained on the first (solver style: y becomes the next x -> redistribute row blocks into
+        # equal blocks; here through an all_gather_object of the row blocks)
+        parts = [None] * world
+        dist.all_gather_object(parts, ys.numpy())
+        y_full = torch.from_numpy(np.concatenate(parts))
+        zs = sh.new_y_shard()
+        sh.spmv(sh.new_x_shard(y_full), zs, alpha=1.0, beta=0.0)
+        gathered = sh.x_full[:sh.global_rows].clone()
         out = [None] * world
-        dist.all_gather_object(out, dict(rank=rank, r0=sh.r0, r1=sh.r1, nnz=sh.nnz, y=ys[:sh.rows].numpy(),
-                                         z=zs[:sh.rows].numpy(), xg=gathered.numpy()))
+        dist.all_gather_object(out, dict(rank=rank, r0=sh.r0, r1=sh.r1, nnz=sh.nnz, y=ys.numpy(), z=zs.numpy(),
+                                         xg=gathered.numpy(), x_block=sh.x_block))
         if rank == 0:
             q.put(out)
     finally:
@@ -77,7 +80,8 @@ def test_sharded_spmv_matches_single_process(world):
     got_z = np.concatenate([d["z"] for d in out])
     assert np.array_equal(got_y, y)          # same oracle arithmetic per row -> bit-identical
     assert np.array_equal(got_z, z)
-    assert np.array_equal(out[0]["xg"], y)   # the last gather carried the y shards
+    assert np.array_equal(out[0]["xg"], y)   # the last gather carried y, reassembled from equal blocks
+    assert all(d["x_block"] == (rows + world - 1) // world for d in out)
     nnzs = [d["nnz"] for d in out]
     assert sum(nnzs) == off[-1]
     assert max(nnzs) - min(nnzs) <= np.diff(off).max() + 1   # balanced up to one row
@@ -90,3 +94,52 @@ def test_split_rows_by_nnz_edge_cases():
     off = torch.zeros(8, dtype=torch.int32)
     b = split_rows_by_nnz(off, 3).tolist()
     assert b[0] == 0 and b[-1] == 7
+
+
+def _cg_worker(rank, world, port, grid, iters, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cudalibrarysamples_b200.cg import conjugate_gradient
+        off, col, val = (torch.from_numpy(a) for a in O.gen_stencil5(grid))
+        n = grid * grid
+        sh = ShardedCsr(off, col, val, rank, world, _oracle_op, balance="rows")
+        ones = torch.ones(n, dtype=torch.float64)
+        b = sh.new_y_shard()
+        sh.spmv(sh.new_x_shard(ones), b, alpha=0.75, beta=0.0)        # b = 0.75 * A * 1  (cg_example.c:405-418)
+        x, norms = conjugate_gradient(sh, b, iters)
+        out = [None] * world
+        dist.all_gather_object(out, dict(rank=rank, x=x.numpy(), norms=norms.numpy()))
+        if rank == 0:
+            q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_cg_converges_like_scipy():
+    """Config 4's solver at toy size: 5-pt Laplacian (cg_example.c:71-128), b = 0.75*A*1, x0 = 0, plain CG, 2 ranks."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    grid, iters, world = 48, 150, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cg_worker, args=(r, world, port, grid, iters, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    out.sort(key=lambda d: d["rank"])
+    x = np.concatenate([d["x"] for d in out])
+    norms = out[0]["norms"]
+    off, col, val = O.gen_stencil5(grid)
+    n = grid * grid
+    A = sp.csr_matrix((val, col, off), shape=(n, n))
+    b = 0.75 * (A @ np.ones(n))
+    assert abs(norms[0] - np.linalg.norm(b)) < 1e-9 * np.linalg.norm(b)
+    assert norms[-1] < 1e-6 * norms[0]                      # converged (exact solution is 0.75 * ones)
+    assert np.linalg.norm(x - 0.75) / np.linalg.norm(0.75 * np.ones(n)) < 1e-6
+    assert np.linalg.norm(b - A @ x) <= 1.01 * norms[-1] + 1e-12   # the recurrence residual is the true residual
