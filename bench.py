@@ -110,9 +110,27 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the samples' host verification loop (spmv_csr_op_example.c:307-318) on the host cores
 # ------------------------------------------------------------------------------------------------------------------
+def pick_threads(off, col, val, x):
+    """Host threads for the CPU arm: the fastest of {allowed CPUs, half of them (physical cores), 32}, probed with two
+    repetitions each -- omp_get_max_threads() counts SMT siblings / CPUs outside the cgroup on some boxes and the loop
+    then runs 20x slower."""
+    from oracle import oracle as O
+    try:
+        allowed = len(os.sched_getaffinity(0))
+    except Exception:
+        allowed = O.max_threads()
+    cands = sorted({max(1, min(allowed, O.max_threads())), max(1, allowed // 2), max(1, min(32, allowed))}, reverse=True)
+    best_t, best = cands[0], float("inf")
+    for t in cands:
+        sec, _, _ = O.time_csr_f64(off, col, val, x, t, reps=2)
+        if sec < best:
+            best_t, best = t, sec
+    return best_t
+
+
 def cpu_reference(off, col, val, x, reps):
     from oracle import oracle as O
-    threads = O.max_threads()
+    threads = pick_threads(off, col, val, x)
     rows = off.size - 1
     best, times, _ = O.time_csr_f64(off, col, val, x, threads, reps=reps)
     gbs = csr_bytes(rows, x.size, col.size) / best / 1e9
@@ -130,7 +148,7 @@ def run_reference_arm(args):
     off, col, val = O.rmat_csr(ROWS_PER_GPU, avg_nnz=AVG_NNZ, seed=42, val_seed=43)
     x = O.uniform(44, ROWS_PER_GPU)
     t_gen = time.time() - t_gen
-    threads = O.max_threads()
+    threads = pick_threads(off, col, val, x)
     rows, nnz = off.size - 1, int(col.size)
     y = np.zeros(rows)
     for _ in range(args.warmup):

@@ -62,6 +62,9 @@ namespace b200 {
 #ifndef B200_CSR_RED_U        // predicated product loads per lane and row before the fall-back loop
 #define B200_CSR_RED_U 2
 #endif
+#ifndef B200_CSR_SOFF16    // stage the tile's rowOff slice as 16-bit offsets (5 KB less shared memory per CTA)
+#define B200_CSR_SOFF16 1
+#endif
 #ifndef B200_CSR_ABLATE   // profiling only: 1 = skip phase 2, 2 = no x gather, 3 = neither (stream only)
 #define B200_CSR_ABLATE 0
 #endif
@@ -69,6 +72,13 @@ constexpr int CSR_TILE_ITEMS = B200_CSR_TILE_ITEMS;  // merge items (row ends + 
 constexpr int CSR_LONG_ROW   = B200_CSR_LONG_ROW;    // rows at least this long may be split between tiles
 constexpr int CSR_BLOCK      = B200_CSR_BLOCK;       // threads per CTA
 constexpr int CSR_SMEM_ELEMS = CSR_TILE_ITEMS + CSR_LONG_ROW;  // max non-zeros a tile can hold
+#if B200_CSR_SOFF16
+typedef short soff_t;      // tile-relative row starts lie in [-1 (clamped), CSR_SMEM_ELEMS + 31] -- fits 16 bits
+static_assert(B200_CSR_TILE_ITEMS + B200_CSR_LONG_ROW + 32 < 32767, "tile too large for 16-bit staged offsets");
+#else
+typedef int soff_t;
+#endif
+__device__ __forceinline__ soff_t to_soff(int v) { return (soff_t)(v < -1 ? -1 : v); }
 constexpr int CSR_BATCH      = B200_CSR_BATCH;  // load steps whose loads are all issued before the first use
 // a tile's element range starts at a multiple of 32 (<= 31 masked lanes) and holds < CSR_SMEM_ELEMS non-zeros
 constexpr int CSR_STEPS      = (CSR_SMEM_ELEMS + 31 + CSR_BLOCK - 1) / CSR_BLOCK;
@@ -170,6 +180,8 @@ struct CsrArgs {
     Scalars<T> s;
     PlanView   plan;
     long long* trace;
+    unsigned   tile_stride;   // one-CTA-per-tile kernels visit tile (blockIdx * tile_stride) % num_tiles (1 = in order)
+    unsigned   num_tiles;
 };
 
 // The phase-2 code runs either on a whole CTA (tile / pipe kernels: __syncthreads) or on the "reduce" warps of a
@@ -391,10 +403,12 @@ __device__ __forceinline__ int tile_phase2(const CsrArgs<T>& a, int b, int rs, i
 template <typename T>
 __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel(const CsrArgs<T> a) {
     __shared__ T   sP[CSR_SMEM_ELEMS];
-    __shared__ int sOff[CSR_SMEM_ELEMS + 1];   // rowOff[rs .. re] - base - ns: a tile spans < CSR_SMEM_ELEMS rows
+    __shared__ soff_t sOff[CSR_SMEM_ELEMS + 1];   // rowOff[rs .. re] - base - ns: a tile spans < CSR_SMEM_ELEMS rows
     __shared__ T   sRed[CSR_BLOCK / 32];
 
-    const int  b  = blockIdx.x;
+    // Tiles are visited in a scattered order: neighbouring tiles of a skewed matrix look alike (R-MAT: long rows first,
+    // thousands of near-empty rows later), and the SM overlaps a gather-heavy tile best with a row-heavy one.
+    const int  b  = (int)(((unsigned long long)blockIdx.x * a.tile_stride) % a.num_tiles);
     const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
     const int  rs = st.x, ns = st.y, re = en.x, ne = en.y;
     const T alpha = a.s.a(), beta = a.s.b();
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
         // the tile's slice of rowOff goes to shared memory first: its latency overlaps the val/col stream, and
         // phase 2 then never waits on global memory
         const int noff = (re < a.rows ? re : a.rows) - rs + 1;
-        for (int i = (int)threadIdx.x; i < noff; i += CSR_BLOCK) sOff[i] = __ldg(a.off + rs + i) - a.base - ns;
+        for (int i = (int)threadIdx.x; i < noff; i += CSR_BLOCK) sOff[i] = to_soff(__ldg(a.off + rs + i) - a.base - ns);
         const int al   = ns & ~31;
         const int lead = ns - al;                 // masked lanes in front of the tile
         const int span = ne - al;                 // elements [lead, span) are live
@@ -447,7 +461,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
     __syncthreads();
     TRACE_STAMP(a, b, 1);
 
-    tile_phase2<T, int, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
+    tile_phase2<T, soff_t, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
     TRACE_STAMP(a, b, 2);
 }
 
@@ -523,7 +537,7 @@ __device__ __forceinline__ void pipe_issue_loads(const CsrArgs<T>& a, int2 st, i
 template <typename T>
 __global__ void __launch_bounds__(CSR_BLOCK, B200_PIPE_MIN_CTAS) csr_pipe_kernel(const CsrArgs<T> a, int num_tiles) {
     __shared__ T   sP[CSR_SMEM_ELEMS];
-    __shared__ int sOff[CSR_SMEM_ELEMS + 1];
+    __shared__ soff_t sOff[CSR_SMEM_ELEMS + 1];
     __shared__ T   sRed[CSR_BLOCK / 32];
 
     int b = blockIdx.x;                      // the launcher guarantees gridDim.x <= num_tiles
@@ -545,10 +559,10 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_PIPE_MIN_CTAS) csr_pipe_kernel
 #pragma unroll
         for (int j = 0; j < PIPE_OFFS; j++) {
             const int i = j * CSR_BLOCK + (int)threadIdx.x;
-            if (i < noff) sOff[i] = t.o[j] - a.base - ns;
+            if (i < noff) sOff[i] = to_soff(t.o[j] - a.base - ns);
         }
         for (int i = PIPE_OFFS * CSR_BLOCK + (int)threadIdx.x; i < noff; i += CSR_BLOCK)      // very row-dense tiles only
-            sOff[i] = __ldg(a.off + rs + i) - a.base - ns;
+            sOff[i] = to_soff(__ldg(a.off + rs + i) - a.base - ns);
 
         // gathers + products
         const int al = ns & ~31, lead = ns - al, span = ne - al;
@@ -576,7 +590,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_PIPE_MIN_CTAS) csr_pipe_kernel
 
         if (has_next) pipe_issue_loads(a, nst, nen, t);   // block-uniform; overlaps phase 2 below
 
-        tile_phase2<T, int, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
+        tile_phase2<T, soff_t, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
         TRACE_STAMP(a, b, 2);
         if (!has_next) break;
         __syncthreads();                                   // sP / sOff are free again
@@ -1004,6 +1018,16 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
     else { a.s.alpha = *(const T*)alpha; a.s.beta = *(const T*)beta; a.s.alpha_dev = nullptr; a.s.beta_dev = nullptr; }
     plan_layout(nt, ws, &a.plan);
     a.trace = nullptr;
+    a.num_tiles = (unsigned)nt;
+    a.tile_stride = 1;
+    if (const char* e = getenv("B200SPMV_TILE_ORDER")) {
+        if (!strcmp(e, "scatter") && nt > 2) {        // stride ~ 0.618 * nt, coprime with nt -> a permutation of the tiles
+            auto gcd = [](uint64_t x, uint64_t y) { while (y) { uint64_t t = x % y; x = y; y = t; } return x; };
+            uint64_t st = (uint64_t)(0.6180339887 * (double)nt) | 1;
+            while (gcd(st, (uint64_t)nt) != 1) st += 2;
+            a.tile_stride = (unsigned)(st % (uint64_t)nt);
+        }
+    }
 #ifdef B200_CSR_TRACE
     a.trace = g_trace_ptr;
 #endif

@@ -82,7 +82,7 @@ if os.environ.get("SWEEP_SET") == "final":
         "rw_b128_occ8": dict(TILE=2048, LONG=512, BLOCK=128, BATCH=4, MIN=8, KERNEL=3, RW=(4, 2)),
     }
 if os.environ.get("SWEEP_SET") == "ab":
-    VARIANTS = {"nobfly": {}, "nobfly_r4": {}, "bfly_occ6": {}, "nobfly_occ6": {}}
+    VARIANTS = {k: {} for k in ['t2048_l256', 't1536_l512_occ6', 't1536_l256_occ6', 't2560_l512_occ4', 't1024_l256_b128_occ10', 't3072_l512_b384_occ3']}
 if os.environ.get("SWEEP_SET") == "ablate":
     VARIANTS = dict(ABL, t2048_b256_k4_occ6=VARIANTS["t2048_b256_k4_occ6"])
 
