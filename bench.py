@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = sys.stdout
 METRIC = "csr_spmv_fp64_effective_hbm_bandwidth"
 UNIT = "GB/s"
 ROWS_PER_GPU = 1_000_000
@@ -168,7 +169,7 @@ def run_reference_arm(args):
         "e2e": {"value": round(gbs, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gflops": round(2 * nnz / (total / args.steps) / 1e9, 3),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 def workload_config(n_gpus, rows, nnz):
@@ -272,7 +273,7 @@ def run_ours(args):
             lop = cs.SpMVOperator(api, "csr", r, c, arrays, preprocess=True)
             make_local.op = lop
             return lop
-        sh = ShardedCsr(off, col, val, rank, world, make_local)
+        sh = ShardedCsr(off, col, val, rank, world, make_local, exchange="allgather")   # R-MAT rows read every x block
         del off, col, val
         torch.cuda.empty_cache()
         xs = sh.new_x_shard(x)
@@ -416,13 +417,22 @@ def run_ours(args):
                 line["roofline"]["traffic"] = json.load(open(prof)).get("csr_tile_kernel_f64_rmat1m_dram_bytes")
             except Exception:
                 pass
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun hints) also write to fd 1, so
+    # everything but our line is re-routed to stderr.
+    global _REAL_STDOUT
+    # Watchdog: a distributed hang must not wedge the GPU box -- dump every thread's stack and exit after the limit.
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "900" if "--impl" in sys.argv and "reference" in sys.argv else "240")), exit=True)
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

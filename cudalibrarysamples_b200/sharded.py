@@ -45,7 +45,8 @@ class ShardedCsr:
     """
 
     def __init__(self, off: torch.Tensor, col: torch.Tensor, val: torch.Tensor, rank: int, world: int,
-                 make_local_op: Callable[[int, int, dict], Callable], group=None, base: int = 0, balance: str = "nnz"):
+                 make_local_op: Callable[[int, int, dict], Callable], group=None, base: int = 0, balance: str = "nnz",
+                 exchange: str = "auto"):
         assert base == 0
         self.rank, self.world, self.group = rank, world, group
         n = off.numel() - 1
@@ -69,6 +70,52 @@ class ShardedCsr:
         self.cols_padded = world * self.x_block
         self.x_full = torch.zeros(self.cols_padded, dtype=val.dtype, device=val.device)
         self.local_op = make_local_op(self.rows, self.cols_padded, dict(off=self.off, col=self.col, val=self.val))
+        self._plan_exchange(exchange)
+
+    def _plan_exchange(self, exchange: str):
+        """Structure-only preprocessing of the exchange step: which part of x does this row block actually read?
+
+        The local columns span [cmin, cmax].  For a banded matrix that is this rank's own block plus a halo (5-pt
+        Poisson 8192^2 on 8 GPUs: 2 x 64 KB instead of 470 MB), so instead of the full all-gather every rank receives,
+        from each owner, only the overlap of [cmin, cmax] with the owner's x block -- straight into x_full, no packing.
+        Falls back to the all-gather when the ranks together need more than half of what the all-gather would move
+        (R-MAT: every rank reads every block)."""
+        world, blk = self.world, self.x_block
+        self.recv_plan, self.send_plan, self.exchange = [], [], "allgather"
+        if world == 1 or exchange == "allgather":
+            return
+        if self.nnz > 0:
+            cmin, cmax = int(self.col.min().item()), int(self.col.max().item()) + 1
+        else:
+            cmin, cmax = 0, 0
+        need = torch.tensor([[cmin, cmax]], dtype=torch.int64, device=self.col.device)
+        allneed = [torch.zeros_like(need) for _ in range(world)]
+        dist.all_gather(allneed, need, group=self.group)
+        ranges = [tuple(int(v) for v in t.flatten().tolist()) for t in allneed]      # (cmin, cmax) of every rank
+        total = 0
+        for g, (lo_need, hi_need) in enumerate(ranges):
+            for h in range(world):
+                if h == g:
+                    continue
+                lo, hi = max(lo_need, h * blk), min(hi_need, (h + 1) * blk)
+                if hi > lo:
+                    total += hi - lo
+                    if g == self.rank:
+                        self.recv_plan.append((h, lo, hi))          # receive x[lo:hi] from its owner h
+                    if h == self.rank:
+                        self.send_plan.append((g, lo - h * blk, hi - h * blk))   # send my block[lo:hi] to g
+        if exchange == "halo" or total * 2 < world * (world - 1) * blk:
+            self.exchange = "halo"
+            self.exchanged_elements = total
+
+    def _halo_exchange(self, x_shard: torch.Tensor):
+        blk = self.x_block
+        self.x_full[self.rank * blk:(self.rank + 1) * blk].copy_(x_shard)
+        ops = [dist.P2POp(dist.isend, x_shard[lo:hi], g, group=self.group) for g, lo, hi in self.send_plan]
+        ops += [dist.P2POp(dist.irecv, self.x_full[lo:hi], h, group=self.group) for h, lo, hi in self.recv_plan]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
 
     def new_x_shard(self, x=None):
         """This rank's equal block of a global vector x (zero-padded at the end of the last block)."""
@@ -88,9 +135,12 @@ class ShardedCsr:
         return t
 
     def gather_x(self, x_shard: torch.Tensor) -> torch.Tensor:
-        """The path's single exchange step: all-gather of the equal x shards."""
+        """The path's single exchange step: all-gather of the equal x shards, or -- when the set-up analysis found that
+        this matrix only reads a narrow column range per rank -- just the needed ranges (halo exchange)."""
         if self.world == 1:
             self.x_full[:self.x_block].copy_(x_shard)
+        elif self.exchange == "halo":
+            self._halo_exchange(x_shard)
         else:
             dist.all_gather_into_tensor(self.x_full, x_shard, group=self.group)
         return self.x_full

@@ -21,6 +21,9 @@ from cudalibrarysamples_b200 import workloads as W
 from cudalibrarysamples_b200.cg import conjugate_gradient
 from cudalibrarysamples_b200.sharded import ShardedCsr
 
+sys.stdout.flush()
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)   # only our JSON line goes to the real stdout
 ap = argparse.ArgumentParser()
 ap.add_argument("--gpus", type=int, default=1)
 ap.add_argument("--grid", type=int, default=8192)
@@ -47,6 +50,7 @@ for impl in ("b200", "cusparse"):
         return cs.SpMVOperator(api, "csr", r, c, arrays, preprocess=True)
 
     sh = ShardedCsr(off, col, val, rank, world, make_local, balance="rows")
+    exch = sh.exchange + (f" ({sh.exchanged_elements * 8} B per step over all ranks)" if sh.exchange == "halo" else "")
     ones = torch.ones(n, dtype=torch.float64, device="cuda")
     b = sh.new_y_shard()
     sh.spmv(sh.new_x_shard(ones), b, alpha=0.75, beta=0.0)      # b = 0.75 * A * 1 (cg_example.c:405-418)
@@ -79,7 +83,8 @@ if rank == 0:
             f"{a.iters} fixed iterations, unpreconditioned, row-sharded over {world} GPU(s), one all-gather of p per iteration",
             "n_gpus": world, "ours": out["b200"], "closed_library_spmv_same_loop": out["cusparse"],
             "speedup": round(out["b200"]["iters_per_s"] / out["cusparse"]["iters_per_s"], 3)}
-    print(json.dumps(line), flush=True)
+    line["exchange"] = exch
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

@@ -76,3 +76,21 @@ def test_reference_samples_bind_spmv_to_the_shim():
     assert "libb200spmv.so" in target("cusparseCreateCsr")
     assert "libcusparse.so.12" in target("cusparseSpSV_solve")
     assert "libcusparse.so.12" in target("cusparseCreate")
+
+
+def test_ld_preload_rebinds_an_already_built_sample():
+    """the stock binary (linked against the real libcusparse only) picks up the shim's SpMV
+    symbols under LD_PRELOAD; everything else stays with the closed library."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "spmv_csr_example.cusparse")
+    lib = os.path.join(ROOT, "cudalibrarysamples_b200", "libb200spmv.so")
+    if not (os.path.exists(exe) and os.path.exists(lib)):
+        import pytest
+        pytest.skip("oracle/_ref or the library not built")
+    env = dict(os.environ, LD_BIND_NOW="1", LD_DEBUG="bindings", LD_PRELOAD=lib)
+    p = subprocess.run([exe], env=env, capture_output=True, text=True)
+    lines = [l for l in p.stderr.splitlines() if "spmv_csr_example.cusparse [0] to" in l]
+    def target(sym):
+        return [l for l in lines if f"`{sym}'" in l][0]
+    for sym in ("cusparseSpMV", "cusparseSpMV_bufferSize", "cusparseSpMV_preprocess", "cusparseCreateCsr", "cusparseCreateDnVec"):
+        assert "libb200spmv.so" in target(sym), sym
+    assert "libcusparse.so.12" in target("cusparseCreate")

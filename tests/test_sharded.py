@@ -36,6 +36,7 @@ def _worker(rank, world, port, rows, q):
         x = torch.from_numpy(O.uniform(5, rows))
         y0 = torch.from_numpy(O.uniform(6, rows))
         sh = ShardedCsr(off, col, val, rank, world, _oracle_op)
+        assert sh.exchange == "allgather"                  # R-MAT: every rank reads every x block
         xs, ys = sh.new_x_shard(x), sh.new_y_shard(y0)
         sh.spmv(xs, ys, alpha=-1.0, beta=1.0)
         # second product chained on the first (solver style: y becomes the next x -> redistribute row blocks into
@@ -105,6 +106,8 @@ def _cg_worker(rank, world, port, grid, iters, q):
         off, col, val = (torch.from_numpy(a) for a in O.gen_stencil5(grid))
         n = grid * grid
         sh = ShardedCsr(off, col, val, rank, world, _oracle_op, balance="rows")
+        assert sh.exchange == "halo"                       # 5-pt stencil: only a halo of `grid` entries per neighbour
+        assert sh.exchanged_elements == 2 * (world - 1) * grid
         ones = torch.ones(n, dtype=torch.float64)
         b = sh.new_y_shard()
         sh.spmv(sh.new_x_shard(ones), b, alpha=0.75, beta=0.0)        # b = 0.75 * A * 1  (cg_example.c:405-418)
