@@ -4,17 +4,24 @@
 // cusparseSpMV_preprocess / cusparseSpMV (reference call sites: cuSPARSE/spmv_csr/spmv_csr_example.c:104-112,
 // cuSPARSE/cg/cg_example.c:156,220,294,415, cuSPARSE/bicgstab/bicgstab_example.c:190,262,315,358,504).
 //
-// Design (see DESIGN.md "CSR kernel"):
-//   * analyze: merge-path style partition of the (rows + nnz) item list into tiles of TILE_ITEMS items.
-//     A tile boundary that falls inside a row shorter than LONG_ROW is rounded down to that row's start,
-//     so ordinary rows never straddle tiles and need no carry/fix-up; only rows >= LONG_ROW are cut, and
-//     their per-tile partial sums are stored and combined, in fixed tile order, by whichever CTA finishes last
-//     (bit-reproducible, single launch, no spin-waits, nothing on the tiles' critical path).
-//   * mv: one CTA per tile.  Phase 1 streams val[]/col_ind[] with L1-bypassing loads (every warp-level
-//     load is one aligned 128 B / 256 B segment, several steps in flight before the first use), gathers x
-//     through L1/L2 and parks the products in shared memory.  Phase 2 reduces each row from shared memory with a group of
-//     g = 1..32 lanes (g picked per tile from its mean row length) and a warp-shuffle tree, and writes y
-//     once.  No tensor cores: 0.125-0.17 flop/B, HBM-bound.
+// Design:
+//   * analyze (csr_partition_kernel): merge-path style partition of the (rows + nnz) item list into tiles of
+//     TILE_ITEMS items.  A tile boundary that falls inside a row shorter than LONG_ROW is rounded down to that
+//     row's start, so ordinary rows never straddle tiles and need no carry / fix-up; only rows >= LONG_ROW are cut.
+//     Their covering tiles store one partial sum each; the partial sums are added in fixed tile order
+//     (bit-reproducible) by csr_fixup_kernel (one-CTA-per-tile kernels; launched with programmatic stream
+//     serialization) or by the last CTA to finish (persistent kernels) -- nothing waits inside a tile.
+//   * mv: four kernels over the same plan, picked at run time (launch_csr):
+//       csr_tile_kernel    one CTA per tile, products staged in shared memory          (default for >= 12 nnz/row)
+//       csr_pipe_kernel    persistent CTAs, next tile's stream prefetched in registers (default for short rows)
+//       csr_ws_kernel      warp-specialised, TMA (cp.async.bulk + mbarrier) fed        (experimental)
+//       csr_rowwise_kernel no shared memory, lane groups own rows                      (experimental)
+//     Common to all: every warp-level load / gather covers 32 consecutive non-zeros (aligned 128 B / 256 B stream
+//     segments through ld.global.nc.L1::no_allocate, fewest distinct lines per x gather), rows are reduced by
+//     groups of g = 1..32 lanes (g picked per tile from its mean row length) with a warp-shuffle tree, y is
+//     written once.  No tensor cores: 0.125-0.17 flop/B.
+//   * What bounds it (profiles/): on scattered matrices not HBM but the SM's L1TEX pipe, which serves x gathers
+//     (~1 distinct line per clock), shared-memory accesses and shuffles strictly in order.
 #include "spmv_common.cuh"
 #include "../../include/b200spmv.h"
 #include <cstdlib>
