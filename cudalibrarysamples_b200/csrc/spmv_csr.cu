@@ -199,11 +199,17 @@ __device__ __forceinline__ void group_sync() {
     else asm volatile("bar.sync %0, %1;" ::"n"(BAR_ID), "n"(BLOCK) : "memory");
 }
 
+// Product k of a tile lives at sP[pidx<PAD>(k)].  PAD skews the layout by one element per 16 so that a thread-per-row
+// walk over rows of equal (power-of-two) length does not put all 32 lanes on one bank (round-2 candidate, see
+// csr_tile_kernel<T, true>).
+template <bool PAD>
+__device__ __forceinline__ int pidx(int k) { return PAD ? k + (k >> 4) : k; }
+
 // Sum sP[lo, hi) with the whole group, fixed order (bit-reproducible). Result valid on group thread 0.
-template <typename T, int BLOCK, int BAR_ID>
+template <typename T, int BLOCK, int BAR_ID, bool PAD = false>
 __device__ __forceinline__ T block_sum_range(const T* sP, int lo, int hi, T* sRed, int tid) {
     T s = T(0);
-    for (int k = lo + tid; k < hi; k += BLOCK) s += sP[k];
+    for (int k = lo + tid; k < hi; k += BLOCK) s += sP[pidx<PAD>(k)];
     s = warp_sum(s);
     group_sync<BLOCK, BAR_ID>();  // sRed reuse
     if ((tid & 31) == 0) sRed[tid >> 5] = s;
@@ -227,7 +233,7 @@ constexpr int RED_ROWS = B200_CSR_RED_ROWS;
 constexpr int RED_ROWS4 = B200_CSR_RED_BUTTERFLY ? 4 : B200_CSR_RED_ROWS;   // groups of >= 4 lanes: 4 rows + transposed butterfly
 constexpr int RED_U    = B200_CSR_RED_U;
 
-template <typename T, typename OT, int G, int ROWS, int U, int BLOCK>
+template <typename T, typename OT, int G, int ROWS, int U, int BLOCK, bool PAD = false>
 __device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, const OT* sOff, int shift, int rs,
                                             int r_first, int nrows, T alpha, T beta, int tid) {
     constexpr int GROUPS = BLOCK / G;
@@ -248,7 +254,7 @@ __device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, co
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int k = k0[i] + u * G;
-                p[i][u] = k < e[i] ? sP[k] : T(0);
+                p[i][u] = k < e[i] ? sP[pidx<PAD>(k)] : T(0);
             }
         T sum[ROWS];
 #pragma unroll
@@ -262,7 +268,7 @@ __device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, co
             for (int kb = k0[i] + U * G; kb < e[i]; kb += U * G) {
                 T q[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) q[u] = kb + u * G < e[i] ? sP[kb + u * G] : T(0);
+                for (int u = 0; u < U; u++) q[u] = kb + u * G < e[i] ? sP[pidx<PAD>(kb + u * G)] : T(0);
 #pragma unroll
                 for (int u = 0; u < U; u++) sum[i] += q[u];
             }
@@ -363,7 +369,7 @@ __device__ __forceinline__ void split_rows_fixup(const CsrArgs<T>& a, T alpha, T
 // ---------------- phase 2: per-row reduction out of shared memory ----------------------------------
 // sP[0 .. ne-ns) holds the tile's products, sOff[i] - shift = rowOff[rs+i] - base - ns for i = 0 .. re-rs (the
 // tile / pipe kernels stage rebased offsets, shift = 0; the TMA-fed kernel stages the raw slice, shift = base + ns).
-template <typename T, typename OT, int BLOCK, int BAR_ID>
+template <typename T, typename OT, int BLOCK, int BAR_ID, bool PAD = false, int G1MAX = 1>
 __device__ __forceinline__ int tile_phase2(const CsrArgs<T>& a, int b, int rs, int ns, int re, int ne, const T* sP,
                                            const OT* sOff, int shift, T* sRed, T alpha, T beta, int tid) {
     if (B200_CSR_ABLATE & 1) { if (sP[tid] == T(1.2345)) a.y[0] = sP[0]; return 0; }
@@ -388,28 +394,31 @@ __device__ __forceinline__ int tile_phase2(const CsrArgs<T>& a, int b, int rs, i
         const int body = tail_beg - head_end;
         const int avg2 = body / (2 * nrows);  // half the mean row length
         if      (avg2 <= 1)  reduce_rows<T, OT, 1, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 2)  reduce_rows<T, OT, 2, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 4)  reduce_rows<T, OT, 4, RED_ROWS4, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 8)  reduce_rows<T, OT, 8, RED_ROWS4, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 16) reduce_rows<T, OT, 16, RED_ROWS4, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else                 reduce_rows<T, OT, 32, 2, 8, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);  // long rows: 256 elements per batch
+        else if (avg2 <= 2)  reduce_rows<T, OT, 2, RED_ROWS, RED_U, BLOCK, PAD>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 4)  reduce_rows<T, OT, 4, RED_ROWS4, RED_U, BLOCK, PAD>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 8)  reduce_rows<T, OT, 8, RED_ROWS4, RED_U, BLOCK, PAD>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 16) reduce_rows<T, OT, 16, RED_ROWS4, RED_U, BLOCK, PAD>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else                 reduce_rows<T, OT, 32, 2, 8, BLOCK, PAD>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);  // long rows: 256 elements per batch
     }
 
     if (head) {  // group-uniform
-        const T hs = block_sum_range<T, BLOCK, BAR_ID>(sP, 0, head_end, sRed, tid);
+        const T hs = block_sum_range<T, BLOCK, BAR_ID, PAD>(sP, 0, head_end, sRed, tid);
         if (tid == 0) a.plan.head_part[b] = (double)hs;
     }
     if (tail) {  // group-uniform
-        const T ts = block_sum_range<T, BLOCK, BAR_ID>(sP, tail_beg, cnt, sRed, tid);
+        const T ts = block_sum_range<T, BLOCK, BAR_ID, PAD>(sP, tail_beg, cnt, sRed, tid);
         if (tid == 0) a.plan.tail_part[b] = (double)ts;
     }
     return (head ? 1 : 0) + (tail ? 1 : 0);   // partial sums this tile deposited (group-uniform)
 }
 
 
-template <typename T>
+// PAD = false: the validated default.  PAD = true (B200SPMV_CSR_KERNEL=tile2): round-2 candidate, NOT yet run on
+// hardware -- skewed product layout + one thread per row for tiles whose mean row length is <= 24, i.e. no shuffles and
+// 16x fewer bank conflicts on equal-length rows (DESIGN.md "Where the next gains are").
+template <typename T, bool PAD>
 __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel(const CsrArgs<T> a) {
-    __shared__ T   sP[CSR_SMEM_ELEMS];
+    __shared__ T   sP[PAD ? CSR_SMEM_ELEMS + CSR_SMEM_ELEMS / 16 + 1 : CSR_SMEM_ELEMS];
     __shared__ soff_t sOff[CSR_SMEM_ELEMS + 1];   // rowOff[rs .. re] - base - ns: a tile spans < CSR_SMEM_ELEMS rows
     __shared__ T   sRed[CSR_BLOCK / 32];
 
@@ -460,7 +469,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
 #pragma unroll
                 for (int k = 0; k < CSR_BATCH; k++) {
                     const int e = (batch + k) * CSR_BLOCK + (int)threadIdx.x;
-                    if (e >= lead && e < span) sP[e - lead] = v[k] * xv[k];
+                    if (e >= lead && e < span) sP[pidx<PAD>(e - lead)] = v[k] * xv[k];
                 }
             }
         }
@@ -468,7 +477,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
     __syncthreads();
     TRACE_STAMP(a, b, 1);
 
-    tile_phase2<T, soff_t, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
+    tile_phase2<T, soff_t, CSR_BLOCK, 0, PAD, PAD ? 12 : 1>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
     TRACE_STAMP(a, b, 2);
 }
 
@@ -1044,12 +1053,15 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
     int mode = B200_CSR_KERNEL;
     if (mode < 0) {
         const char* e = getenv("B200SPMV_CSR_KERNEL");   // read per call (~0.1 us) so tests can switch kernels
-        const int env_mode = !e ? -1 : !strcmp(e, "tile") ? 0 : !strcmp(e, "pipe") ? 1 : !strcmp(e, "ws") ? 2 : !strcmp(e, "rowwise") ? 3 : -1;
+        const int env_mode = !e ? -1 : !strcmp(e, "tile") ? 0 : !strcmp(e, "pipe") ? 1 : !strcmp(e, "ws") ? 2 : !strcmp(e, "rowwise") ? 3 : !strcmp(e, "tile2") ? 4 : -1;
         mode = env_mode >= 0 ? env_mode : (nnz >= 12 * rows ? 0 : 1);
     }
     if (mode == 2 && (((uintptr_t)col | (uintptr_t)val | (uintptr_t)off) & 15) != 0) mode = 1;   // TMA needs 16 B alignment
     if (mode == 0) {
-        csr_tile_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+        csr_tile_kernel<T, false><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+        launch_fixup<T>(a, stream);
+    } else if (mode == 4) {
+        csr_tile_kernel<T, true><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
         launch_fixup<T>(a, stream);
     } else if (mode == 3) {
         csr_rowwise_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
