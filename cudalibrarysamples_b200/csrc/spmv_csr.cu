@@ -481,6 +481,202 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
     TRACE_STAMP(a, b, 2);
 }
 
+// ================================================================================================
+// Round-2 candidate (B200SPMV_CSR_KERNEL=hyb) -- compiled, never selected automatically, NOT yet run on hardware.
+// Emulated lane by lane on the CPU (tests/test_hyb_emulation.py) to pin the row bookkeeping.
+//
+// Per tile: if its rows are long on average (>= HYB_DENSE non-zeros per row; 41 % of the R-MAT tiles, 77 % of its
+// non-zeros sit in such rows) the products never touch shared memory: every warp owns a contiguous chunk of the tile
+// (still 32 consecutive non-zeros per load / gather instruction), lanes accumulate the current row across the load
+// steps in a register, and a row costs one xor-butterfly (10 shuffles) when it ends.  Rows that cross chunk borders
+// are stitched together from <= 8 per-warp partials after one barrier.  Other tiles take the padded thread-per-row
+// path of csr_tile_kernel<T, true>.  Goal: reduction term of the L1TEX budget 0.44 -> <= 0.2 wavefronts / non-zero.
+// ================================================================================================
+constexpr int HYB_DENSE  = 64;
+constexpr int HYB_WSTEPS = (CSR_SMEM_ELEMS + 31 + 255) / 256;        // 32-element steps per warp, worst case
+constexpr int HYB_BATCH  = 4;
+constexpr int HYB_HAS_FIRST = 1, HYB_FIRST_ENDS = 2, HYB_HAS_OPEN = 4;
+
+template <typename T>
+__device__ __forceinline__ T warp_allsum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_hyb_kernel(const CsrArgs<T> a) {
+    static_assert(CSR_BLOCK == 256, "the chunk bookkeeping assumes 8 warps");
+    __shared__ T      sP[CSR_SMEM_ELEMS + CSR_SMEM_ELEMS / 16 + 1];
+    __shared__ soff_t sOff[CSR_SMEM_ELEMS + 1];
+    __shared__ T      sRed[CSR_BLOCK / 32];
+    __shared__ T      sFirst[8], sOpen[8];
+    __shared__ int    sOpenRow[8], sFlags[8];
+
+    const int  b  = (int)(((unsigned long long)blockIdx.x * a.tile_stride) % a.num_tiles);
+    const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
+    const int  rs = st.x, ns = st.y, re = en.x, ne = en.y;
+    const T alpha = a.s.a(), beta = a.s.b();
+    cudaTriggerProgrammaticLaunchCompletion();
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const int noff = (re < a.rows ? re : a.rows) - rs + 1;
+    for (int i = tid; i < noff; i += CSR_BLOCK) sOff[i] = to_soff(__ldg(a.off + rs + i) - a.base - ns);
+    const int al = ns & ~31, lead = ns - al, span = ne - al, cnt = ne - ns;
+    const int* colp = a.col + al;
+    const T*   valp = a.val + al;
+    const int  nr = re - rs;                                   // row starts S(0..nr) = sOff[0..nr] lie in this tile
+    const bool dense = cnt >= HYB_DENSE * (nr > 0 ? nr : 1);   // block-uniform, from the tile descriptor alone
+
+    if (!dense) {
+        // ---------------- shared-memory path: same as csr_tile_kernel<T, true> ----------------
+#pragma unroll
+        for (int batch = 0; batch < CSR_ITERS; batch += CSR_BATCH) {
+            if (batch * CSR_BLOCK < span) {
+                int c[CSR_BATCH];
+                T   v[CSR_BATCH], xv[CSR_BATCH];
+#pragma unroll
+                for (int k = 0; k < CSR_BATCH; k++) {
+                    const int e = (batch + k) * CSR_BLOCK + tid;
+                    const bool live = e >= lead && e < span;
+                    c[k] = live ? ldg_stream(colp + e) : a.base;
+                    v[k] = live ? ldg_stream(valp + e) : T(0);
+                }
+#pragma unroll
+                for (int k = 0; k < CSR_BATCH; k++) {
+                    const int e = (batch + k) * CSR_BLOCK + tid;
+                    xv[k] = (e >= lead && e < span) ? __ldg(a.x + (c[k] - a.base)) : T(0);
+                }
+#pragma unroll
+                for (int k = 0; k < CSR_BATCH; k++) {
+                    const int e = (batch + k) * CSR_BLOCK + tid;
+                    if (e >= lead && e < span) sP[pidx<true>(e - lead)] = v[k] * xv[k];
+                }
+            }
+        }
+        __syncthreads();
+        tile_phase2<T, soff_t, CSR_BLOCK, 0, true, 12>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, tid);
+        return;
+    }
+
+    // ---------------- register path: warp w owns steps [s0, s0 + steps_w) of the tile ----------------
+    const int steps_total = (span + 31) >> 5;
+    const int steps_w = (steps_total + 7) >> 3;                // block-uniform, 1 .. HYB_WSTEPS
+    const int s0 = warp * steps_w;
+    const int cs = max(s0 * 32 - lead, 0);                     // chunk = tile-relative positions [cs, ce)
+    const int ce = min((s0 + steps_w) * 32 - lead, cnt);
+    const bool active = cs < ce;
+
+    // walk state (warp-uniform)
+    int  cur = 0, seg_beg = cs, cur_end = 0x7fffffff, flags = 0, open_row = 0;
+    bool started = true;
+    T    acc = T(0), first = T(0), open = T(0);
+
+#pragma unroll
+    for (int kb = 0; kb < HYB_WSTEPS; kb += HYB_BATCH) {
+        if (kb < steps_w) {                                    // block-uniform
+            int c[HYB_BATCH];
+            T   v[HYB_BATCH], p[HYB_BATCH];
+#pragma unroll
+            for (int k = 0; k < HYB_BATCH; k++) {
+                const int e = (s0 + kb + k) * 32 + lane;
+                const bool live = kb + k < steps_w && e >= lead && e < span;
+                c[k] = live ? ldg_stream(colp + e) : a.base;
+                v[k] = live ? ldg_stream(valp + e) : T(0);
+            }
+#pragma unroll
+            for (int k = 0; k < HYB_BATCH; k++) {
+                const int e = (s0 + kb + k) * 32 + lane;
+                const bool live = kb + k < steps_w && e >= lead && e < span;
+                p[k] = live ? v[k] * __ldg(a.x + (c[k] - a.base)) : T(0);
+            }
+            if (kb == 0) {
+                __syncthreads();                               // sOff is staged; the first batch is already in flight
+                if (active) {
+                    // first row whose end lies beyond the previous warps' territory: rows j with S(j) <= lo ended earlier
+                    const int lo = warp == 0 ? -1 : cs;
+                    int n = 0;
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const int j = lane + 1 + 32 * r;
+                        n += __popc(__ballot_sync(0xffffffffu, j <= nr && (int)sOff[j] <= lo));
+                    }
+                    cur = n;
+                    const int s_cur = (int)sOff[cur];
+                    started = warp == 0 ? s_cur >= 0 : s_cur == cs;      // s_cur < 0: the tile starts inside row rs
+                    cur_end = cur < nr ? (int)sOff[cur + 1] : 0x7fffffff;
+                }
+            }
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < HYB_BATCH; k++) {
+                    if (kb + k < steps_w) {                    // block-uniform
+                        const int pos = (s0 + kb + k) * 32 + lane - lead;
+                        const int step_end = min((s0 + kb + k) * 32 + 32 - lead, cnt);
+                        while (cur_end <= step_end) {          // row `cur` ends inside this step (warp-uniform)
+                            acc += (pos >= seg_beg && pos < cur_end) ? p[k] : T(0);
+                            const T tot = warp_allsum(acc);
+                            if (started) {
+                                if (lane == 0) {
+                                    T* yp = a.y + rs + cur;
+                                    *yp = axpby(alpha, tot, beta, yp);
+                                }
+                            } else {
+                                first = tot;
+                                flags |= HYB_HAS_FIRST | HYB_FIRST_ENDS;
+                            }
+                            seg_beg = cur_end;
+                            cur++;
+                            cur_end = cur < nr ? (int)sOff[cur + 1] : 0x7fffffff;
+                            started = true;
+                            acc = T(0);
+                        }
+                        acc += (pos >= seg_beg && pos < step_end) ? p[k] : T(0);
+                    }
+                }
+            }
+        }
+    }
+    if (active && seg_beg < ce) {                              // the row in progress continues past this chunk
+        const T tot = warp_allsum(acc);
+        if (started) { open = tot; open_row = cur; flags |= HYB_HAS_OPEN; }
+        else         { first = tot; flags |= HYB_HAS_FIRST; }
+    }
+    if (lane == 0) { sFirst[warp] = first; sOpen[warp] = open; sOpenRow[warp] = open_row; sFlags[warp] = flags; }
+    __syncthreads();
+
+    if (tid < 8) {
+        const int w = tid, f = sFlags[w];
+        if (f & HYB_HAS_OPEN) {                                // a row that started in warp w and ran on
+            T tot = sOpen[w];
+            bool ended = false;
+            for (int v = w + 1; v < 8; v++) {
+                const int fv = sFlags[v];
+                if (!(fv & HYB_HAS_FIRST)) break;
+                tot += sFirst[v];
+                if (fv & HYB_FIRST_ENDS) { ended = true; break; }
+            }
+            if (ended) {
+                T* yp = a.y + rs + sOpenRow[w];
+                *yp = axpby(alpha, tot, beta, yp);
+            } else {
+                a.plan.tail_part[b] = (double)tot;             // only the tile's last row can stay open: split row
+            }
+        }
+        if (w == 0 && (f & HYB_HAS_FIRST)) {                   // the tile starts inside row rs: split row
+            T tot = sFirst[0];
+            if (!(f & HYB_FIRST_ENDS))
+                for (int v = 1; v < 8; v++) {
+                    const int fv = sFlags[v];
+                    if (!(fv & HYB_HAS_FIRST)) break;
+                    tot += sFirst[v];
+                    if (fv & HYB_FIRST_ENDS) break;
+                }
+            a.plan.head_part[b] = (double)tot;
+        }
+    }
+}
+
 // One-CTA-per-tile launches leave the split rows to this small second launch.  (Measured alternatives: an arrival
 // counter bumped by every CTA, or only by the CTAs that deposited partial sums, costs 5-25 % on R-MAT because a whole
 // CTA waits for one atomic round trip; the extra launch costs ~4 us.)
@@ -1053,7 +1249,7 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
     int mode = B200_CSR_KERNEL;
     if (mode < 0) {
         const char* e = getenv("B200SPMV_CSR_KERNEL");   // read per call (~0.1 us) so tests can switch kernels
-        const int env_mode = !e ? -1 : !strcmp(e, "tile") ? 0 : !strcmp(e, "pipe") ? 1 : !strcmp(e, "ws") ? 2 : !strcmp(e, "rowwise") ? 3 : !strcmp(e, "tile2") ? 4 : -1;
+        const int env_mode = !e ? -1 : !strcmp(e, "tile") ? 0 : !strcmp(e, "pipe") ? 1 : !strcmp(e, "ws") ? 2 : !strcmp(e, "rowwise") ? 3 : !strcmp(e, "tile2") ? 4 : !strcmp(e, "hyb") ? 5 : -1;
         mode = env_mode >= 0 ? env_mode : (nnz >= 12 * rows ? 0 : 1);
     }
     if (mode == 2 && (((uintptr_t)col | (uintptr_t)val | (uintptr_t)off) & 15) != 0) mode = 1;   // TMA needs 16 B alignment
@@ -1062,6 +1258,9 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
         launch_fixup<T>(a, stream);
     } else if (mode == 4) {
         csr_tile_kernel<T, true><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+        launch_fixup<T>(a, stream);
+    } else if (mode == 5) {
+        csr_hyb_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
         launch_fixup<T>(a, stream);
     } else if (mode == 3) {
         csr_rowwise_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
