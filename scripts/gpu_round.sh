@@ -18,3 +18,4 @@ echo "== other configs";  timeout 400 python scripts/bench_formats.py > $OUT/${T
 echo "== CSR kernels on the standard matrices"; SWEEP_SET=none timeout 400 python scripts/sweep.py run rmat1m rmat10m uniform1m stencil5_4096 > $OUT/${TAG}_sweep_default.txt 2>&1; grep -E "==|us " $OUT/${TAG}_sweep_default.txt
 echo "== ncu launch list"; ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/${TAG}_launches_bench.csv python bench.py --steps 20 --warmup 3 --no-cpu > $OUT/${TAG}_bench_ncu.log 2>&1
 echo "== ncu --set full (dominant kernel)"; ncu --set full --clock-control none --import-source on -k regex:"csr_tile_kernel|csr_pipe_kernel" -s 2 -c 1 -o $OUT/prof_${TAG}_csr python scripts/prof_spmv.py --impl b200 --workload rmat1m > $OUT/${TAG}_ncu.log 2>&1; tail -n 1 $OUT/${TAG}_ncu.log
+echo "== every CSR kernel of the library (incl. the unselected candidates tile2 / hyb)"; SWEEP_SET=kernels timeout 400 python scripts/sweep.py run rmat1m rmat10m uniform1m stencil5_4096 > $OUT/${TAG}_sweep_kernels.txt 2>&1; grep -E "==|us " $OUT/${TAG}_sweep_kernels.txt

@@ -150,6 +150,8 @@ def run(workloads, variants=None, steps=100):
     results = {}
     libs = [("default", None)] + [(t, os.path.join(VDIR, f"libb200spmv_{t}.so")) for t in VARIANTS if (variants is None or t in variants)]
     libs = [(t, p) for t, p in libs if p is None or os.path.exists(p)]
+    if os.environ.get("SWEEP_SET") == "kernels":     # every CSR kernel of the default library, picked through the env switch
+        libs = [("default", None)] + [("kernel:" + k, None) for k in ("tile", "pipe", "tile2", "hyb", "rowwise", "ws")]
     for wl in workloads:
         rows, off, col, val = make_workload(wl)
         nnz = int(col.numel())
@@ -158,6 +160,10 @@ def run(workloads, variants=None, steps=100):
         ref = None
         print(f"== {wl}: rows={rows} nnz={nnz} alg_bytes={nbytes / 1e6:.1f} MB", flush=True)
         for tag, path in libs + [("cusparse", "closed")]:
+            if tag.startswith("kernel:"):
+                os.environ["B200SPMV_CSR_KERNEL"] = tag.split(":")[1]
+            else:
+                os.environ.pop("B200SPMV_CSR_KERNEL", None)
             api = cs.Api("cusparse") if tag == "cusparse" else cs.Api("b200", lib_path=path)
             op = cs.SpMVOperator(api, "csr", rows, rows, dict(off=off, col=col, val=val))
             y = torch.zeros(rows, dtype=torch.float64, device="cuda")
