@@ -249,6 +249,9 @@ def run_ours(args):
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; the contract is ONE JSON line on stdout
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
+        # Plain stream order for the fix-up launch next to NCCL kernels: the programmatic early launch buys ~0.5 us on
+        # 100 us, and one 4-GPU run of this script hung for reasons we could not reproduce (profiles/README.md).
+        os.environ.setdefault("B200SPMV_NO_PDL", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     sampler.start()

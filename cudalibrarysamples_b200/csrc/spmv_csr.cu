@@ -701,7 +701,8 @@ static void launch_fixup(const CsrArgs<T>& a, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, csr_fixup_kernel<T>, a) != cudaSuccess) {
+    const char* no_pdl = getenv("B200SPMV_NO_PDL");            // plain stream order instead (multi-process runs set it)
+    if ((no_pdl && no_pdl[0] == '1') || cudaLaunchKernelEx(&cfg, csr_fixup_kernel<T>, a) != cudaSuccess) {
         (void)cudaGetLastError();
         csr_fixup_kernel<T><<<16, 256, 0, stream>>>(a);      // plain stream order is always correct
     }
