@@ -120,11 +120,11 @@ def _cg_worker(rank, world, port, grid, iters, q):
         dist.destroy_process_group()
 
 
-def test_sharded_cg_converges_like_scipy():
-    """Config 4's solver at toy size: 5-pt Laplacian (cg_example.c:71-128), b = 0.75*A*1, x0 = 0, plain CG, 2 ranks."""
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_cg_converges_like_scipy(world):
+    """Config 4's solver at toy size: 5-pt Laplacian (cg_example.c:71-128), b = 0.75*A*1, x0 = 0, plain CG."""
     import scipy.sparse as sp
-    import scipy.sparse.linalg as spla
-    grid, iters, world = 48, 150, 2
+    grid, iters = 48, 150
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
     port = _free_port()
