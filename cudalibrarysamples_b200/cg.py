@@ -44,14 +44,14 @@ def conjugate_gradient(sh: ShardedCsr, b_shard: torch.Tensor, iters: int, x0_sha
     for _ in range(iters):
         sh.spmv(p, t, alpha=1.0, beta=0.0)             # T = A * P      (cg_example.c:220-224)
         denom = _dot(t, p, world, group)
-        alpha = delta / denom
-        x.add_(p * alpha)                              # X += alpha P   (cg_example.c:236-239)
-        r.sub_(t * alpha)                              # R -= alpha T   (cg_example.c:241-244)
+        alpha = delta / denom                          # 1-element device tensors: no host sync in the loop
+        x.addcmul_(p, alpha)                           # X += alpha P   (cg_example.c:236-239), one pass, no temporary
+        r.addcmul_(t, alpha, value=-1.0)               # R -= alpha T   (cg_example.c:241-244)
         delta_new = _dot(r, r, world, group)
         norms.append(delta_new.sqrt())
         if tol is not None and float(norms[-1]) < tol * float(norms[0]):
             break
         beta = delta_new / delta
-        p.mul_(beta).add_(r)                           # P = beta P + R (cg_example.c:280-286)
+        torch.addcmul(r, p, beta, out=p)               # P = beta P + R (cg_example.c:280-286), one pass
         delta = delta_new
     return x, torch.cat(norms)
