@@ -1,0 +1,24 @@
+// config.h -- run-time switches of libb200spmv.so, read from the environment ONCE (first use) and changeable
+// afterwards only through b200spmv_set_option() (tests / tuning sweeps).  Nothing on the launch path calls getenv().
+#pragma once
+
+namespace b200 {
+
+struct Config {
+    int csr_kernel  = -1;   // B200SPMV_CSR_KERNEL = tile|pipe|ws|rowwise|seg ; -1 = run-time choice
+    int tile_scatter = 0;   // B200SPMV_TILE_ORDER = scatter
+    int pdl         = 0;    // B200SPMV_PDL = 1: launch the CSR fix-up kernel with programmatic stream serialization
+    int seg_dense   = 24;   // B200SPMV_SEG_DENSE: csr_seg_kernel takes the register path for tiles with >= this many nnz per row
+    int sell_generic = 0;   // B200SPMV_SELL_GENERIC = 1: never use the slice-32 specialisation
+    int coo_kernel  = -1;   // B200SPMV_COO_KERNEL = tile|seg ; -1 = default (seg)
+};
+
+Config& config();
+
+// counters a test can read: how many SpMV calls ran on our kernels / were handed to the closed library
+struct Stats {
+    unsigned long long native_calls = 0, forwarded_calls = 0, analyze_calls = 0;
+};
+Stats& stats();
+
+}  // namespace b200

@@ -21,6 +21,7 @@
 #include <unordered_map>
 
 #include "../../include/b200spmv.h"
+#include "config.h"
 
 namespace {
 
@@ -108,7 +109,7 @@ struct MatInfo {
     cusparseIndexBase_t  base = CUSPARSE_INDEX_BASE_ZERO;
     cudaDataType         vtype = CUDA_R_32F;
     int64_t              sell_values_size = 0, slice_size = 0;
-    void*                plan_buffer = nullptr;  // externalBuffer currently holding this matrix' CSR plan
+    void*                plan_buffer = nullptr;  // externalBuffer holding this matrix' CSR plan: set ONLY by cusparseSpMV_preprocess
 };
 struct VecInfo {
     int64_t      size = 0;
@@ -180,7 +181,7 @@ bool supported(cusparseOperation_t op, const MatInfo& m, const VecInfo& x, const
     if (dtype_of(m.vtype) < 0 || x.vtype != m.vtype || y.vtype != m.vtype || compute != m.vtype) return false;
     if (m.off_type != CUSPARSE_INDEX_32I || m.col_type != CUSPARSE_INDEX_32I) return false;
     if (m.format != CUSPARSE_FORMAT_CSR && m.format != CUSPARSE_FORMAT_COO && m.format != CUSPARSE_FORMAT_SLICED_ELLPACK) return false;
-    if (m.rows >= INT32_MAX || m.cols >= INT32_MAX || m.nnz >= INT32_MAX - 8) return false;
+    if (m.rows >= INT32_MAX || m.cols >= INT32_MAX || m.nnz >= INT32_MAX - 65536) return false;
     return true;
 }
 
@@ -404,22 +405,21 @@ cusparseStatus_t cusparseSpMV_bufferSize(cusparseHandle_t handle, cusparseOperat
     return CUSPARSE_STATUS_SUCCESS;
 }
 
-static cusparseStatus_t ensure_csr_plan(cudaStream_t stream, cusparseConstSpMatDescr_t matA, const MatInfo& m, void* buffer,
-                                        bool force) {
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (!force && m.plan_buffer == buffer) {
-            auto ow = g_plan_owner.find(buffer);
-            if (ow != g_plan_owner.end() && ow->second == m.uid) return CUSPARSE_STATUS_SUCCESS;
-        }
-    }
-    int rc = b200spmv_csr_analyze((void*)stream, m.rows, m.nnz, m.offsets, (int32_t)m.base, buffer);
-    if (rc != 0) return to_status(rc);
+// The CSR tile plan lives in the caller's externalBuffer.  It is TRUSTED on a later cusparseSpMV only if that buffer
+// was handed to cusparseSpMV_preprocess for this very descriptor (the documented contract: the buffer must then be
+// kept, unmodified, and passed to cusparseSpMV).  Without a preprocess call the buffer is plain scratch to the real
+// library -- a caller may share it with SpSV / SpMM or get the same address back from a caching allocator with other
+// contents -- so the plan is rebuilt on EVERY call (one ~3 us partition kernel on the same stream, graph-capturable).
+static cusparseStatus_t build_csr_plan(cudaStream_t stream, const MatInfo& m, void* buffer) {
+    b200::stats().analyze_calls++;
+    return to_status(b200spmv_csr_analyze((void*)stream, m.rows, m.nnz, m.offsets, (int32_t)m.base, buffer));
+}
+
+static bool plan_is_trusted(const MatInfo& m, void* buffer) {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_mats.find((const void*)matA);
-    if (it != g_mats.end()) it->second.plan_buffer = buffer;
-    g_plan_owner[buffer] = m.uid;
-    return CUSPARSE_STATUS_SUCCESS;
+    if (m.plan_buffer != buffer) return false;
+    auto ow = g_plan_owner.find(buffer);
+    return ow != g_plan_owner.end() && ow->second == m.uid;
 }
 
 cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t handle, cusparseOperation_t opA, const void* alpha,
@@ -439,7 +439,15 @@ cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t handle, cusparseOperat
     cusparseStatus_t st = R.cusparseGetStream(handle, &stream);
     if (st != CUSPARSE_STATUS_SUCCESS) return st;
     logf("preprocess(csr plan)", m);
-    return ensure_csr_plan(stream, matA, m, externalBuffer, /*force=*/true);
+    st = build_csr_plan(stream, m, externalBuffer);
+    if (st != CUSPARSE_STATUS_SUCCESS) return st;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_mats.find((const void*)matA);
+    if (it != g_mats.end()) {
+        it->second.plan_buffer = externalBuffer;
+        g_plan_owner[externalBuffer] = it->second.uid;     // a buffer holds one matrix' plan: the latest preprocess wins
+    }
+    return CUSPARSE_STATUS_SUCCESS;
 }
 
 cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, const void* alpha,
@@ -447,11 +455,15 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
                               cusparseDnVecDescr_t vecY, cudaDataType computeType, cusparseSpMVAlg_t alg,
                               void* externalBuffer) {
     Real& R = real();
-    if (R.forward) return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
+    if (R.forward) {
+        b200::stats().forwarded_calls++;
+        return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
+    }
     if (!handle || !matA || !vecX || !vecY || !alpha || !beta) return CUSPARSE_STATUS_INVALID_VALUE;
     MatInfo m; VecInfo x, y;
     if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType)) {
         if (R.log) fprintf(stderr, "[b200spmv] SpMV forwarded to libcusparse (unsupported combination)\n");
+        b200::stats().forwarded_calls++;
         return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
     }
     if (x.size != m.cols || y.size != m.rows) return CUSPARSE_STATUS_INVALID_VALUE;
@@ -467,12 +479,17 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
     if (m.format == CUSPARSE_FORMAT_CSR) {
         if (m.rows == 0) return CUSPARSE_STATUS_SUCCESS;
         if (!externalBuffer || ((uintptr_t)externalBuffer & 15)) {
-            // No room for a plan (caller ignored bufferSize): let the real library handle it.
+            // No room for a plan (caller ignored bufferSize): let the real library handle it -- loudly under
+            // B200SPMV_LOG, and counted (b200spmv_get_stats) so a test can prove the hot path never takes this exit.
+            if (R.log) fprintf(stderr, "[b200spmv] SpMV forwarded to libcusparse (NULL or misaligned externalBuffer)\n");
+            b200::stats().forwarded_calls++;
             return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
         }
-        st = ensure_csr_plan(stream, matA, m, externalBuffer, /*force=*/false);
-        if (st != CUSPARSE_STATUS_SUCCESS) return st;
-        logf("SpMV csr_tile_kernel", m);
+        if (!plan_is_trusted(m, externalBuffer)) {
+            st = build_csr_plan(stream, m, externalBuffer);
+            if (st != CUSPARSE_STATUS_SUCCESS) return st;
+        }
+        logf("SpMV csr kernels", m);
         rc = b200spmv_csr_mv((void*)stream, dt, m.rows, m.cols, m.nnz, m.offsets, m.col_ind, m.values, (int32_t)m.base, alpha,
                              beta, on_dev, x.values, (void*)y.values, externalBuffer);
     } else if (m.format == CUSPARSE_FORMAT_COO) {
@@ -484,6 +501,7 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
         rc = b200spmv_sell_mv((void*)stream, dt, m.rows, m.cols, m.slice_size, m.offsets, m.col_ind, m.values,
                               (int32_t)m.base, alpha, beta, on_dev, x.values, (void*)y.values, externalBuffer);
     }
+    b200::stats().native_calls++;
     return to_status(rc);
 }
 

@@ -6,8 +6,10 @@
 // SELL replaces cusparse::sellmv_v1_kernel behind cusparseSpMV for cusparseCreateSlicedEll descriptors
 //   (cuSPARSE/spmv_sell/spmv_sell_example.c:103-122): column-major inside each slice, padding col = -1.
 #include "spmv_common.cuh"
+#include "config.h"
 #include "../../include/b200spmv.h"
 #include <cstdlib>
+#include <mutex>
 
 #ifndef B200_SELL_UNROLL
 #define B200_SELL_UNROLL 8
@@ -125,6 +127,99 @@ __global__ void __launch_bounds__(COO_BLOCK) coo_tile_kernel(const CooArgs<T> a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// coo_seg_kernel (default): no shared memory, no barriers -- every warp owns a contiguous chunk of COO_SEG_STEPS x 32
+// entries and walks it with a per-lane accumulator, exactly like csr_seg_kernel, except that the row boundaries come
+// straight from the row indices: lane l ends a run iff row[l] != row[l + 1].  A 32-entry step inside one row costs
+// nothing (acc += product); a step with run ends costs one butterfly for the first run (accumulator + head of the
+// step) plus a segmented shuffle scan with as many levels as the longest remaining run needs, and ONE atomic (RED.ADD
+// at L2) per run end.  For row-sorted input (spmv_coo_example.c:48-49) that is one atomic per row and chunk instead of
+// one per 8 entries; unsorted input stays correct (every run of equal row indices is just added where it belongs).
+// Measured motivation: round 1's coo_tile_kernel was 0.66x the closed library on R-MAT 1M (125.8 vs 82.8 us).
+// ------------------------------------------------------------------------------------------------
+#ifndef B200_COO_SEG_STEPS
+#define B200_COO_SEG_STEPS 8
+#endif
+#ifndef B200_COO_SEG_BATCH
+#define B200_COO_SEG_BATCH 4
+#endif
+#ifndef B200_COO_SEG_MIN_CTAS
+#define B200_COO_SEG_MIN_CTAS 4
+#endif
+constexpr int COO_SEG_STEPS = B200_COO_SEG_STEPS, COO_SEG_BATCH = B200_COO_SEG_BATCH;
+constexpr int COO_SEG_CHUNK = 32 * COO_SEG_STEPS;
+static_assert(COO_SEG_STEPS % COO_SEG_BATCH == 0, "steps per chunk must be a multiple of the batch");
+
+template <typename T>
+__device__ __forceinline__ T coo_warp_allsum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(COO_BLOCK, B200_COO_SEG_MIN_CTAS) coo_seg_kernel(const CooArgs<T> a) {
+    const int lane = (int)threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * (COO_BLOCK / 32) + ((int)threadIdx.x >> 5);
+    const long long c0 = wid * COO_SEG_CHUNK;
+    if (c0 >= a.nnz) return;                                  // warp-uniform
+    const int n0 = (int)c0;
+    const int n1 = min(n0 + COO_SEG_CHUNK, a.nnz);            // this warp's entries [n0, n1)
+    const T alpha = a.s.a();
+    T acc = T(0);
+
+    int r[COO_SEG_BATCH], rn[COO_SEG_BATCH], c[COO_SEG_BATCH];
+    T   v[COO_SEG_BATCH];
+    auto issue = [&](int kb) {
+#pragma unroll
+        for (int k = 0; k < COO_SEG_BATCH; k++) {
+            const int e = n0 + (kb + k) * 32 + lane;
+            const bool live = e < n1;
+            r[k]  = live ? ldg_stream(a.row + e) : -1;
+            rn[k] = (live && e + 1 < n1) ? ldg_stream(a.row + e + 1) : -2;    // the chunk's last entry always ends a run
+            c[k]  = live ? ldg_stream(a.col + e) : a.base;
+            v[k]  = live ? ldg_stream(a.val + e) : T(0);
+        }
+    };
+    issue(0);
+#pragma unroll
+    for (int kb = 0; kb < COO_SEG_STEPS; kb += COO_SEG_BATCH) {
+        if (n0 + kb * 32 < n1) {                              // warp-uniform
+            T   p[COO_SEG_BATCH];
+            int rr[COO_SEG_BATCH];
+            unsigned mm[COO_SEG_BATCH];
+#pragma unroll
+            for (int k = 0; k < COO_SEG_BATCH; k++) {
+                const bool live = n0 + (kb + k) * 32 + lane < n1;
+                p[k]  = live ? v[k] * __ldg(a.x + (c[k] - a.base)) : T(0);
+                rr[k] = r[k];
+                mm[k] = __ballot_sync(0xffffffffu, live && r[k] != rn[k]);
+            }
+            if (kb + COO_SEG_BATCH < COO_SEG_STEPS && n0 + (kb + COO_SEG_BATCH) * 32 < n1) issue(kb + COO_SEG_BATCH);
+#pragma unroll
+            for (int k = 0; k < COO_SEG_BATCH; k++) {
+                const unsigned m = mm[k];
+                if (m == 0u) { acc += p[k]; continue; }       // the whole step lies inside one run
+                const int e1 = __ffs(m) - 1, ek = 31 - __clz(m);
+                const T t1 = coo_warp_allsum(acc + (lane <= e1 ? p[k] : T(0)));
+                T q = (lane > e1 && lane <= ek) ? p[k] : T(0);
+                if (m & (m - 1u)) {                           // more runs end: segmented inclusive scan
+                    const unsigned below = m & ((1u << lane) - 1u);
+                    const int dist = (lane > e1 && lane <= ek) ? lane - (32 - __clz(below)) : 0;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        if (__ballot_sync(0xffffffffu, dist >= d) == 0u) break;
+                        const T t = __shfl_up_sync(0xffffffffu, q, d);
+                        if (dist >= d) q += t;
+                    }
+                }
+                if ((m >> lane) & 1u) atomicAdd(a.y + (rr[k] - a.base), alpha * (lane == e1 ? t1 : q));
+                acc = lane > ek ? p[k] : T(0);
+            }
+        }
+    }
+}
+
 template <typename T>
 static int launch_coo(cudaStream_t stream, int64_t rows, int64_t nnz, const void* row, const void* col, const void* val,
                       int base, const void* alpha, const void* beta, int on_device, const void* x, void* y) {
@@ -136,14 +231,22 @@ static int launch_coo(cudaStream_t stream, int64_t rows, int64_t nnz, const void
         int64_t blocks = (rows + threads - 1) / threads;
         if (blocks > 148 * 16) blocks = 148 * 16;
         scale_y_kernel<T><<<(unsigned)blocks, threads, 0, stream>>>((T*)y, rows, s);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
     }
     if (nnz > 0) {
         CooArgs<T> a;
         a.row = (const int*)row; a.col = (const int*)col; a.val = (const T*)val; a.x = (const T*)x; a.y = (T*)y;
         a.base = base; a.nnz = (int)nnz; a.s = s;
         a.vec_ok = (((uintptr_t)row | (uintptr_t)col | (uintptr_t)val) & 15) == 0;
-        const unsigned blocks = (unsigned)((nnz + COO_TILE - 1) / COO_TILE);
-        coo_tile_kernel<T><<<blocks, COO_BLOCK, 0, stream>>>(a);
+        if (config().coo_kernel == 0) {
+            const unsigned blocks = (unsigned)((nnz + COO_TILE - 1) / COO_TILE);
+            coo_tile_kernel<T><<<blocks, COO_BLOCK, 0, stream>>>(a);
+        } else {
+            const int64_t per_cta = (int64_t)COO_SEG_CHUNK * (COO_BLOCK / 32);
+            const unsigned blocks = (unsigned)((nnz + per_cta - 1) / per_cta);
+            coo_seg_kernel<T><<<blocks, COO_BLOCK, 0, stream>>>(a);
+        }
     }
     return (int)cudaGetLastError();
 }
@@ -299,20 +402,27 @@ static int launch_sell(cudaStream_t stream, int64_t rows, int64_t slice_size, co
     a.base = base; a.rows = (int)rows; a.slice_size = (int)slice_size;
     if (on_device) { a.s.alpha = T(0); a.s.beta = T(0); a.s.alpha_dev = (const T*)alpha; a.s.beta_dev = (const T*)beta; }
     else { a.s.alpha = *(const T*)alpha; a.s.beta = *(const T*)beta; a.s.alpha_dev = nullptr; a.s.beta_dev = nullptr; }
-    static int per_sm[2] = {0, 0};   // resident CTAs per SM, per value type
+    // persistent grid of the generic kernel: SMs x resident CTAs, cached per (device, value type) under a lock
+    static int grid_cache[64][2];
+    static std::mutex mu;
     const int ti = sizeof(T) == 4 ? 0 : 1;
-    if (!per_sm[ti]) {
-        int n = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)sell_row_kernel<T, 0>, SELL_BLOCK, 0);
-        per_sm[ti] = n < 1 ? 1 : n;
-    }
-    int sms = 148, dev = 0;
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t persistent;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        int& g = grid_cache[dev & 63][ti];
+        if (!g) {
+            int n = 1, sms = 148;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)sell_row_kernel<T, 0>, SELL_BLOCK, 0);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            g = sms * (n < 1 ? 1 : n);
+        }
+        persistent = (int64_t)g * B200_SELL_WAVES;
+    }
     int64_t blocks = (rows + SELL_BLOCK - 1) / SELL_BLOCK;
-    const int64_t persistent = (int64_t)sms * per_sm[ti] * B200_SELL_WAVES;
     if (blocks > persistent) blocks = persistent;
-    if (slice_size == 32 && !getenv("B200SPMV_SELL_GENERIC")) {
+    if (slice_size == 32 && !config().sell_generic) {
         const int64_t all = (rows + SELL_BLOCK - 1) / SELL_BLOCK;
         sell32_kernel<T><<<(unsigned)all, SELL_BLOCK, 0, stream>>>(a);
     } else {

@@ -23,9 +23,11 @@
 //   * What bounds it (profiles/): on scattered matrices not HBM but the SM's L1TEX pipe, which serves x gathers
 //     (~1 distinct line per clock), shared-memory accesses and shuffles strictly in order.
 #include "spmv_common.cuh"
+#include "config.h"
 #include "../../include/b200spmv.h"
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace b200 {
 
@@ -189,6 +191,8 @@ struct CsrArgs {
     long long* trace;
     unsigned   tile_stride;   // one-CTA-per-tile kernels visit tile (blockIdx * tile_stride) % num_tiles (1 = in order)
     unsigned   num_tiles;
+    int        seg_dense;     // csr_seg_kernel: tiles with >= seg_dense non-zeros per row end take the register path
+    int        pdl;           // 1: the fix-up kernel is launched with programmatic stream serialization (opt-in)
 };
 
 // The phase-2 code runs either on a whole CTA (tile / pipe kernels: __syncthreads) or on the "reduce" warps of a
@@ -199,17 +203,11 @@ __device__ __forceinline__ void group_sync() {
     else asm volatile("bar.sync %0, %1;" ::"n"(BAR_ID), "n"(BLOCK) : "memory");
 }
 
-// Product k of a tile lives at sP[pidx<PAD>(k)].  PAD skews the layout by one element per 16 so that a thread-per-row
-// walk over rows of equal (power-of-two) length does not put all 32 lanes on one bank (round-2 candidate, see
-// csr_tile_kernel<T, true>).
-template <bool PAD>
-__device__ __forceinline__ int pidx(int k) { return PAD ? k + (k >> 4) : k; }
-
 // Sum sP[lo, hi) with the whole group, fixed order (bit-reproducible). Result valid on group thread 0.
-template <typename T, int BLOCK, int BAR_ID, bool PAD = false>
+template <typename T, int BLOCK, int BAR_ID>
 __device__ __forceinline__ T block_sum_range(const T* sP, int lo, int hi, T* sRed, int tid) {
     T s = T(0);
-    for (int k = lo + tid; k < hi; k += BLOCK) s += sP[pidx<PAD>(k)];
+    for (int k = lo + tid; k < hi; k += BLOCK) s += sP[k];
     s = warp_sum(s);
     group_sync<BLOCK, BAR_ID>();  // sRed reuse
     if ((tid & 31) == 0) sRed[tid >> 5] = s;
@@ -233,7 +231,7 @@ constexpr int RED_ROWS = B200_CSR_RED_ROWS;
 constexpr int RED_ROWS4 = B200_CSR_RED_BUTTERFLY ? 4 : B200_CSR_RED_ROWS;   // groups of >= 4 lanes: 4 rows + transposed butterfly
 constexpr int RED_U    = B200_CSR_RED_U;
 
-template <typename T, typename OT, int G, int ROWS, int U, int BLOCK, bool PAD = false>
+template <typename T, typename OT, int G, int ROWS, int U, int BLOCK>
 __device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, const OT* sOff, int shift, int rs,
                                             int r_first, int nrows, T alpha, T beta, int tid) {
     constexpr int GROUPS = BLOCK / G;
@@ -254,7 +252,7 @@ __device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, co
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int k = k0[i] + u * G;
-                p[i][u] = k < e[i] ? sP[pidx<PAD>(k)] : T(0);
+                p[i][u] = k < e[i] ? sP[k] : T(0);
             }
         T sum[ROWS];
 #pragma unroll
@@ -268,7 +266,7 @@ __device__ __forceinline__ void reduce_rows(const CsrArgs<T>& a, const T* sP, co
             for (int kb = k0[i] + U * G; kb < e[i]; kb += U * G) {
                 T q[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) q[u] = kb + u * G < e[i] ? sP[pidx<PAD>(kb + u * G)] : T(0);
+                for (int u = 0; u < U; u++) q[u] = kb + u * G < e[i] ? sP[kb + u * G] : T(0);
 #pragma unroll
                 for (int u = 0; u < U; u++) sum[i] += q[u];
             }
@@ -369,7 +367,7 @@ __device__ __forceinline__ void split_rows_fixup(const CsrArgs<T>& a, T alpha, T
 // ---------------- phase 2: per-row reduction out of shared memory ----------------------------------
 // sP[0 .. ne-ns) holds the tile's products, sOff[i] - shift = rowOff[rs+i] - base - ns for i = 0 .. re-rs (the
 // tile / pipe kernels stage rebased offsets, shift = 0; the TMA-fed kernel stages the raw slice, shift = base + ns).
-template <typename T, typename OT, int BLOCK, int BAR_ID, bool PAD = false, int G1MAX = 1>
+template <typename T, typename OT, int BLOCK, int BAR_ID>
 __device__ __forceinline__ int tile_phase2(const CsrArgs<T>& a, int b, int rs, int ns, int re, int ne, const T* sP,
                                            const OT* sOff, int shift, T* sRed, T alpha, T beta, int tid) {
     if (B200_CSR_ABLATE & 1) { if (sP[tid] == T(1.2345)) a.y[0] = sP[0]; return 0; }
@@ -394,31 +392,29 @@ __device__ __forceinline__ int tile_phase2(const CsrArgs<T>& a, int b, int rs, i
         const int body = tail_beg - head_end;
         const int avg2 = body / (2 * nrows);  // half the mean row length
         if      (avg2 <= 1)  reduce_rows<T, OT, 1, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 2)  reduce_rows<T, OT, 2, RED_ROWS, RED_U, BLOCK, PAD>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 4)  reduce_rows<T, OT, 4, RED_ROWS4, RED_U, BLOCK, PAD>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 8)  reduce_rows<T, OT, 8, RED_ROWS4, RED_U, BLOCK, PAD>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else if (avg2 <= 16) reduce_rows<T, OT, 16, RED_ROWS4, RED_U, BLOCK, PAD>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
-        else                 reduce_rows<T, OT, 32, 2, 8, BLOCK, PAD>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);  // long rows: 256 elements per batch
+        else if (avg2 <= 2)  reduce_rows<T, OT, 2, RED_ROWS, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 4)  reduce_rows<T, OT, 4, RED_ROWS4, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 8)  reduce_rows<T, OT, 8, RED_ROWS4, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else if (avg2 <= 16) reduce_rows<T, OT, 16, RED_ROWS4, RED_U, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);
+        else                 reduce_rows<T, OT, 32, 2, 8, BLOCK>(a, sP, sOff, shift, rs, r_first, nrows, alpha, beta, tid);  // long rows: 256 elements per batch
     }
 
     if (head) {  // group-uniform
-        const T hs = block_sum_range<T, BLOCK, BAR_ID, PAD>(sP, 0, head_end, sRed, tid);
+        const T hs = block_sum_range<T, BLOCK, BAR_ID>(sP, 0, head_end, sRed, tid);
         if (tid == 0) a.plan.head_part[b] = (double)hs;
     }
     if (tail) {  // group-uniform
-        const T ts = block_sum_range<T, BLOCK, BAR_ID, PAD>(sP, tail_beg, cnt, sRed, tid);
+        const T ts = block_sum_range<T, BLOCK, BAR_ID>(sP, tail_beg, cnt, sRed, tid);
         if (tid == 0) a.plan.tail_part[b] = (double)ts;
     }
     return (head ? 1 : 0) + (tail ? 1 : 0);   // partial sums this tile deposited (group-uniform)
 }
 
 
-// PAD = false: the validated default.  PAD = true (B200SPMV_CSR_KERNEL=tile2): round-2 candidate, NOT yet run on
-// hardware -- skewed product layout + one thread per row for tiles whose mean row length is <= 24, i.e. no shuffles and
-// 16x fewer bank conflicts on equal-length rows (DESIGN.md "Where the next gains are").
-template <typename T, bool PAD>
+// One CTA per tile; products of the whole tile staged in shared memory, rows reduced by lane groups (tile_phase2).
+template <typename T>
 __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel(const CsrArgs<T> a) {
-    __shared__ T   sP[PAD ? CSR_SMEM_ELEMS + CSR_SMEM_ELEMS / 16 + 1 : CSR_SMEM_ELEMS];
+    __shared__ T   sP[CSR_SMEM_ELEMS];
     __shared__ soff_t sOff[CSR_SMEM_ELEMS + 1];   // rowOff[rs .. re] - base - ns: a tile spans < CSR_SMEM_ELEMS rows
     __shared__ T   sRed[CSR_BLOCK / 32];
 
@@ -429,7 +425,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
     const int  rs = st.x, ns = st.y, re = en.x, ne = en.y;
     const T alpha = a.s.a(), beta = a.s.b();
     TRACE_STAMP(a, b, 0); TRACE_SMID(a, b);
-    cudaTriggerProgrammaticLaunchCompletion();   // lets csr_fixup_kernel get resident early (it still waits for our completion)
+    if (a.pdl) cudaTriggerProgrammaticLaunchCompletion();   // lets csr_fixup_kernel get resident early (it still waits for our completion)
 
     // ---------------- phase 1: stream val/col, gather x, park products in shared memory -------------
     // Lane l of a warp handles element (step*BLOCK + warp*32 + l): every load/gather instruction covers 32
@@ -469,7 +465,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
 #pragma unroll
                 for (int k = 0; k < CSR_BATCH; k++) {
                     const int e = (batch + k) * CSR_BLOCK + (int)threadIdx.x;
-                    if (e >= lead && e < span) sP[pidx<PAD>(e - lead)] = v[k] * xv[k];
+                    if (e >= lead && e < span) sP[e - lead] = v[k] * xv[k];
                 }
             }
         }
@@ -477,25 +473,45 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_tile_kernel
     __syncthreads();
     TRACE_STAMP(a, b, 1);
 
-    tile_phase2<T, soff_t, CSR_BLOCK, 0, PAD, PAD ? 12 : 1>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
+    tile_phase2<T, soff_t, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, (int)threadIdx.x);
     TRACE_STAMP(a, b, 2);
 }
 
 // ================================================================================================
-// Round-2 candidate (B200SPMV_CSR_KERNEL=hyb) -- compiled, never selected automatically, NOT yet run on hardware.
-// Emulated lane by lane on the CPU (tests/test_hyb_emulation.py) to pin the row bookkeeping.
+// csr_seg_kernel ("seg"): one CTA per tile, but the products of ROW-SPARSE tiles never touch shared memory.
 //
-// Per tile: if its rows are long on average (>= HYB_DENSE non-zeros per row; 41 % of the R-MAT tiles, 77 % of its
-// non-zeros sit in such rows) the products never touch shared memory: every warp owns a contiguous chunk of the tile
-// (still 32 consecutive non-zeros per load / gather instruction), lanes accumulate the current row across the load
-// steps in a register, and a row costs one xor-butterfly (10 shuffles) when it ends.  Rows that cross chunk borders
-// are stitched together from <= 8 per-warp partials after one barrier.  Other tiles take the padded thread-per-row
-// path of csr_tile_kernel<T, true>.  Goal: reduction term of the L1TEX budget 0.44 -> <= 0.2 wavefronts / non-zero.
+// Why (profiles/ncu_r1_summary_table.md, ncu of csr_tile_kernel on R-MAT 1M): the kernel is bound by the SM's L1TEX
+// data pipe (19.4 M wavefronts per launch: 12.4 M global, 1.1 M STS, 2.3 M LDS, 3.6 M SHFL), and a third of that is the
+// row reduction: every product makes a round trip through shared memory and every row -- whatever its length -- pays
+// a full shuffle tree of its tile's group size.  On skewed matrices 81 % of the non-zeros sit in rows >= 32 long.
+//
+// Here every warp owns a CONTIGUOUS chunk of the tile (still 32 consecutive non-zeros per load / gather instruction)
+// and walks it step by step with a per-lane accumulator:
+//   * a 32-element step in which no row ends costs nothing: acc += product;
+//   * a step in which rows end: the lanes hold a window of the next 32 row ends (from the staged rowOff slice); one
+//     ballot finds the k rows ending in this step, one REDUX.OR builds the mask of their end lanes, ONE butterfly
+//     gives the first row's total (accumulator + head of the step), a segmented shuffle scan -- only as many levels as
+//     the longest remaining segment needs -- gives the others, and lane j fetches the total of row cur + j with one
+//     shuffle and writes y[row cur + j] (coalesced; empty rows fall out as zero sums).
+// Rows that cross chunk borders are stitched from <= 2 partials per warp by one thread after a barrier; rows that cross
+// TILE borders (>= LONG_ROW) deposit head/tail partials for csr_fixup_kernel exactly like the other kernels.
+// Modelled on the R-MAT 1M structure (scripts/model_seg_cost.py): 2.8 M shuffle wavefronts instead of 7.0 M
+// shared + shuffle wavefronts.  Tiles with many short rows (more than one row per SEG_DENSE non-zeros) keep the
+// staged-product path of csr_tile_kernel: there nearly every step ends several rows and the scan would cost more.
 // ================================================================================================
-constexpr int HYB_DENSE  = 64;
-constexpr int HYB_WSTEPS = (CSR_SMEM_ELEMS + 31 + 255) / 256;        // 32-element steps per warp, worst case
-constexpr int HYB_BATCH  = 4;
-constexpr int HYB_HAS_FIRST = 1, HYB_FIRST_ENDS = 2, HYB_HAS_OPEN = 4;
+#ifndef B200_SEG_BATCH
+#define B200_SEG_BATCH 4
+#endif
+#ifndef B200_SEG_MIN_CTAS
+#define B200_SEG_MIN_CTAS B200_TILE_MIN_CTAS
+#endif
+#ifndef B200_SEG_STAGED      // 0 (sweeps): no staged-product fallback, every tile takes the register path and the CTA needs
+#define B200_SEG_STAGED 1    //   5 KB instead of 26 KB of shared memory (more of the unified L1 left for x)
+#endif
+constexpr int SEG_WARPS  = CSR_BLOCK / 32;
+constexpr int SEG_WSTEPS = ((CSR_SMEM_ELEMS + 31 + 31) / 32 + SEG_WARPS - 1) / SEG_WARPS;   // 32-element steps per warp, worst case
+constexpr int SEG_BATCH  = B200_SEG_BATCH;
+constexpr int SEG_BIG    = 32767;                 // "this row never ends here": sentinel behind the staged row starts
 
 template <typename T>
 __device__ __forceinline__ T warp_allsum(T v) {
@@ -504,32 +520,57 @@ __device__ __forceinline__ T warp_allsum(T v) {
     return v;
 }
 
+// Number of j in [0, nr) with S[j + 1] <= lo  (S = staged row starts, non-decreasing), by the whole warp: two levels of
+// a 32-ary search instead of log2(nr) dependent probes.
+__device__ __forceinline__ int warp_count_ended(const soff_t* S, int nr, int lo, int lane) {
+    if (nr <= 0) return 0;
+    const int stride = (nr + 31) >> 5;
+    const int blk_lo = lane * stride;
+    const int blk_hi = min(blk_lo + stride, nr);                         // block [blk_lo, blk_hi)
+    const bool full = blk_lo < nr && (int)S[blk_hi] <= lo;               // the block's last row has ended
+    const int nb = __popc(__ballot_sync(0xffffffffu, full));
+    int cnt = nb * stride;
+    if (cnt >= nr) return nr;
+    const int hi = min(cnt + stride, nr);
+    int extra = 0;
+    for (int j0 = cnt; j0 < hi; j0 += 32) {                              // warp-uniform trip count (<= 3)
+        const int j = j0 + lane;
+        extra += __popc(__ballot_sync(0xffffffffu, j < hi && (int)S[j + 1] <= lo));
+    }
+    return cnt + extra;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_hyb_kernel(const CsrArgs<T> a) {
-    static_assert(CSR_BLOCK == 256, "the chunk bookkeeping assumes 8 warps");
-    __shared__ T      sP[CSR_SMEM_ELEMS + CSR_SMEM_ELEMS / 16 + 1];
-    __shared__ soff_t sOff[CSR_SMEM_ELEMS + 1];
-    __shared__ T      sRed[CSR_BLOCK / 32];
-    __shared__ T      sFirst[8], sOpen[8];
-    __shared__ int    sOpenRow[8], sFlags[8];
+__global__ void __launch_bounds__(CSR_BLOCK, B200_SEG_MIN_CTAS) csr_seg_kernel(const CsrArgs<T> a) {
+#if B200_SEG_STAGED
+    __shared__ T      sP[CSR_SMEM_ELEMS];
+    __shared__ T      sRed[SEG_WARPS];
+#endif
+    __shared__ soff_t sOff[CSR_SMEM_ELEMS + 1 + 34];      // row starts of the tile + 33 sentinels for the lane window
+    __shared__ T      sFirst[SEG_WARPS], sOpen[SEG_WARPS];
+    __shared__ int    sFirstRow[SEG_WARPS];               // >= 0: the chunk ended at least one row; its first one is this row
 
     const int  b  = (int)(((unsigned long long)blockIdx.x * a.tile_stride) % a.num_tiles);
     const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
     const int  rs = st.x, ns = st.y, re = en.x, ne = en.y;
     const T alpha = a.s.a(), beta = a.s.b();
-    cudaTriggerProgrammaticLaunchCompletion();
+    if (a.pdl) cudaTriggerProgrammaticLaunchCompletion();
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    const int noff = (re < a.rows ? re : a.rows) - rs + 1;
+    const int nr  = re - rs;                  // rows [rs, re) END in this tile (merge path: a row's end item follows its non-zeros)
+    const int cnt = ne - ns;
+    const int noff = nr + 1;                  // S(0 .. nr); re <= rows, so rowOff[re] exists
     for (int i = tid; i < noff; i += CSR_BLOCK) sOff[i] = to_soff(__ldg(a.off + rs + i) - a.base - ns);
-    const int al = ns & ~31, lead = ns - al, span = ne - al, cnt = ne - ns;
+    if (tid < 34) sOff[noff + tid] = (soff_t)SEG_BIG;
+
+    const int al = ns & ~31, lead = ns - al, span = ne - al;
     const int* colp = a.col + al;
     const T*   valp = a.val + al;
-    const int  nr = re - rs;                                   // row starts S(0..nr) = sOff[0..nr] lie in this tile
-    const bool dense = cnt >= HYB_DENSE * (nr > 0 ? nr : 1);   // block-uniform, from the tile descriptor alone
+#if B200_SEG_STAGED
+    const bool sparse = cnt >= a.seg_dense * (nr > 0 ? nr : 1);   // block-uniform, from the tile descriptor alone
 
-    if (!dense) {
-        // ---------------- shared-memory path: same as csr_tile_kernel<T, true> ----------------
+    if (!sparse) {
+        // ---------------- many short rows: products staged in shared memory, as in csr_tile_kernel ----------------
 #pragma unroll
         for (int batch = 0; batch < CSR_ITERS; batch += CSR_BATCH) {
             if (batch * CSR_BLOCK < span) {
@@ -550,130 +591,165 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_hyb_kernel(
 #pragma unroll
                 for (int k = 0; k < CSR_BATCH; k++) {
                     const int e = (batch + k) * CSR_BLOCK + tid;
-                    if (e >= lead && e < span) sP[pidx<true>(e - lead)] = v[k] * xv[k];
+                    if (e >= lead && e < span) sP[e - lead] = v[k] * xv[k];
                 }
             }
         }
         __syncthreads();
-        tile_phase2<T, soff_t, CSR_BLOCK, 0, true, 12>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, tid);
+        tile_phase2<T, soff_t, CSR_BLOCK, 0>(a, b, rs, ns, re, ne, sP, sOff, 0, sRed, alpha, beta, tid);
         return;
     }
+#else
+    if (cnt == 0) {                           // only empty rows end here: y = beta * y (a split row that ends here deposits 0)
+        __syncthreads();
+        for (int j = tid; j < nr; j += CSR_BLOCK) {
+            if (j == 0 && (int)sOff[0] < 0) a.plan.head_part[b] = 0.0;
+            else { T* yp = a.y + rs + j; *yp = axpby(alpha, T(0), beta, yp); }
+        }
+        return;
+    }
+#endif
 
-    // ---------------- register path: warp w owns steps [s0, s0 + steps_w) of the tile ----------------
+    // ---------------- row-sparse tile: warp w owns steps [s0, s0 + steps_w) of the tile ----------------
     const int steps_total = (span + 31) >> 5;
-    const int steps_w = (steps_total + 7) >> 3;                // block-uniform, 1 .. HYB_WSTEPS
+    const int steps_w = (steps_total + SEG_WARPS - 1) / SEG_WARPS;       // block-uniform, 1 .. SEG_WSTEPS
     const int s0 = warp * steps_w;
-    const int cs = max(s0 * 32 - lead, 0);                     // chunk = tile-relative positions [cs, ce)
+    const int cs = max(s0 * 32 - lead, 0);                               // chunk = tile-relative positions [cs, ce)
     const int ce = min((s0 + steps_w) * 32 - lead, cnt);
     const bool active = cs < ce;
 
-    // walk state (warp-uniform)
-    int  cur = 0, seg_beg = cs, cur_end = 0x7fffffff, flags = 0, open_row = 0;
-    bool started = true;
-    T    acc = T(0), first = T(0), open = T(0);
+    // walk state; cur / frow / acc_live are warp-uniform, ws / we / acc per lane
+    int  cur = 0, frow = -1;
+    int  ws = SEG_BIG, we = SEG_BIG;          // lane j: start / end (exclusive) of row cur + j, tile-relative
+    T    acc = T(0), first = T(0);
+    bool acc_live = false;                    // some lane of acc may be non-zero
+
+    int c[SEG_BATCH];
+    T   v[SEG_BATCH];
+#pragma unroll
+    for (int k = 0; k < SEG_BATCH; k++) {     // first batch of the stream in flight before anything else
+        const int e = (s0 + k) * 32 + lane;
+        const bool live = k < steps_w && e >= lead && e < span;
+        c[k] = live ? ldg_stream(colp + e) : a.base;
+        v[k] = live ? ldg_stream(valp + e) : T(0);
+    }
 
 #pragma unroll
-    for (int kb = 0; kb < HYB_WSTEPS; kb += HYB_BATCH) {
-        if (kb < steps_w) {                                    // block-uniform
-            int c[HYB_BATCH];
-            T   v[HYB_BATCH], p[HYB_BATCH];
+    for (int kb = 0; kb < SEG_WSTEPS; kb += SEG_BATCH) {
+        if (kb < steps_w) {                                              // block-uniform
+            T p[SEG_BATCH];
 #pragma unroll
-            for (int k = 0; k < HYB_BATCH; k++) {
-                const int e = (s0 + kb + k) * 32 + lane;
-                const bool live = kb + k < steps_w && e >= lead && e < span;
-                c[k] = live ? ldg_stream(colp + e) : a.base;
-                v[k] = live ? ldg_stream(valp + e) : T(0);
-            }
-#pragma unroll
-            for (int k = 0; k < HYB_BATCH; k++) {
+            for (int k = 0; k < SEG_BATCH; k++) {
                 const int e = (s0 + kb + k) * 32 + lane;
                 const bool live = kb + k < steps_w && e >= lead && e < span;
                 p[k] = live ? v[k] * __ldg(a.x + (c[k] - a.base)) : T(0);
             }
-            if (kb == 0) {
-                __syncthreads();                               // sOff is staged; the first batch is already in flight
-                if (active) {
-                    // first row whose end lies beyond the previous warps' territory: rows j with S(j) <= lo ended earlier
-                    const int lo = warp == 0 ? -1 : cs;
-                    int n = 0;
+            if (kb + SEG_BATCH < SEG_WSTEPS && kb + SEG_BATCH < steps_w) {   // next batch of the stream (block-uniform)
 #pragma unroll
-                    for (int r = 0; r < 2; r++) {
-                        const int j = lane + 1 + 32 * r;
-                        n += __popc(__ballot_sync(0xffffffffu, j <= nr && (int)sOff[j] <= lo));
-                    }
-                    cur = n;
-                    const int s_cur = (int)sOff[cur];
-                    started = warp == 0 ? s_cur >= 0 : s_cur == cs;      // s_cur < 0: the tile starts inside row rs
-                    cur_end = cur < nr ? (int)sOff[cur + 1] : 0x7fffffff;
+                for (int k = 0; k < SEG_BATCH; k++) {
+                    const int e = (s0 + kb + SEG_BATCH + k) * 32 + lane;
+                    const bool live = kb + SEG_BATCH + k < steps_w && e >= lead && e < span;
+                    c[k] = live ? ldg_stream(colp + e) : a.base;
+                    v[k] = live ? ldg_stream(valp + e) : T(0);
+                }
+            }
+            if (kb == 0) {
+                __syncthreads();                                         // sOff is staged; the loads above are in flight
+                if (active) {
+                    // rows whose end lies at or before the chunk start were finished by earlier warps (warp 0: none)
+                    cur = warp == 0 ? 0 : warp_count_ended(sOff, nr, cs, lane);
+                    ws = (int)sOff[cur + lane];
+                    we = (int)sOff[cur + lane + 1];
                 }
             }
             if (active) {
 #pragma unroll
-                for (int k = 0; k < HYB_BATCH; k++) {
-                    if (kb + k < steps_w) {                    // block-uniform
-                        const int pos = (s0 + kb + k) * 32 + lane - lead;
-                        const int step_end = min((s0 + kb + k) * 32 + 32 - lead, cnt);
-                        while (cur_end <= step_end) {          // row `cur` ends inside this step (warp-uniform)
-                            acc += (pos >= seg_beg && pos < cur_end) ? p[k] : T(0);
-                            const T tot = warp_allsum(acc);
-                            if (started) {
-                                if (lane == 0) {
-                                    T* yp = a.y + rs + cur;
-                                    *yp = axpby(alpha, tot, beta, yp);
+                for (int k = 0; k < SEG_BATCH; k++) {
+                    if (kb + k < steps_w) {                              // block-uniform
+                        const int sb = (s0 + kb + k) * 32 - lead;        // tile-relative position of lane 0
+                        if (sb < ce) {                                   // warp-uniform (the last warp's chunk may end early)
+                            const int step_end = min(sb + 32, ce);
+                            T pend = p[k];
+                            for (;;) {
+                                const int kk = __popc(__ballot_sync(0xffffffffu, we <= step_end));   // rows ending in this step
+                                if (kk == 0) break;
+                                const bool has = lane < kk && we > max(ws, cs);      // row cur + lane has elements in this chunk
+                                const unsigned m = __reduce_or_sync(0xffffffffu, has ? 1u << (we - 1 - sb) : 0u);
+                                T res = T(0);
+                                if (m != 0u) {
+                                    const int e1 = __ffs(m) - 1, ek = 31 - __clz(m);
+                                    const T t1 = warp_allsum(acc + (lane <= e1 ? pend : T(0)));
+                                    T q = (lane > e1 && lane <= ek) ? pend : T(0);
+                                    if (m & (m - 1u)) {                              // more rows end: segmented inclusive scan
+                                        const unsigned below = m & ((1u << lane) - 1u);
+                                        const int dist = (lane > e1 && lane <= ek) ? lane - (32 - __clz(below)) : 0;   // lanes before me in my segment
+#pragma unroll
+                                        for (int d = 1; d < 32; d <<= 1) {
+                                            if (__ballot_sync(0xffffffffu, dist >= d) == 0u) break;      // no segment that long
+                                            const T t = __shfl_up_sync(0xffffffffu, q, d);
+                                            if (dist >= d) q += t;
+                                        }
+                                    }
+                                    res = lane == e1 ? t1 : q;
+                                    acc = T(0);
+                                    acc_live = false;
+                                    pend = lane > ek ? pend : T(0);
                                 }
-                            } else {
-                                first = tot;
-                                flags |= HYB_HAS_FIRST | HYB_FIRST_ENDS;
+                                T val = __shfl_sync(0xffffffffu, res, has ? we - 1 - sb : 0);
+                                val = has ? val : T(0);
+                                if (frow < 0) {                          // the chunk's first row end goes to the stitcher
+                                    first = val;                         // lane 0 keeps it (only lane 0 stores it)
+                                    frow = cur;
+                                    if (lane > 0 && lane < kk) {
+                                        T* yp = a.y + rs + cur + lane;
+                                        *yp = axpby(alpha, val, beta, yp);
+                                    }
+                                } else if (lane < kk) {
+                                    T* yp = a.y + rs + cur + lane;
+                                    *yp = axpby(alpha, val, beta, yp);
+                                }
+                                cur += kk;
+                                ws = (int)sOff[cur + lane];
+                                we = (int)sOff[cur + lane + 1];
+                                if (kk < 32) break;
                             }
-                            seg_beg = cur_end;
-                            cur++;
-                            cur_end = cur < nr ? (int)sOff[cur + 1] : 0x7fffffff;
-                            started = true;
-                            acc = T(0);
+                            acc += pend;
+                            acc_live = acc_live || __ballot_sync(0xffffffffu, pend != T(0)) != 0u;
                         }
-                        acc += (pos >= seg_beg && pos < step_end) ? p[k] : T(0);
                     }
                 }
             }
         }
     }
-    if (active && seg_beg < ce) {                              // the row in progress continues past this chunk
-        const T tot = warp_allsum(acc);
-        if (started) { open = tot; open_row = cur; flags |= HYB_HAS_OPEN; }
-        else         { first = tot; flags |= HYB_HAS_FIRST; }
+    {
+        const T open = acc_live ? warp_allsum(acc) : T(0);               // the row in progress continues past this chunk
+        if (lane == 0) {
+            if (frow >= 0) { sFirst[warp] = first; sOpen[warp] = open; }
+            else           { sFirst[warp] = open;  sOpen[warp] = T(0); }  // no row ended: the whole chunk is one partial
+            sFirstRow[warp] = frow;
+        }
     }
-    if (lane == 0) { sFirst[warp] = first; sOpen[warp] = open; sOpenRow[warp] = open_row; sFlags[warp] = flags; }
     __syncthreads();
 
-    if (tid < 8) {
-        const int w = tid, f = sFlags[w];
-        if (f & HYB_HAS_OPEN) {                                // a row that started in warp w and ran on
-            T tot = sOpen[w];
-            bool ended = false;
-            for (int v = w + 1; v < 8; v++) {
-                const int fv = sFlags[v];
-                if (!(fv & HYB_HAS_FIRST)) break;
-                tot += sFirst[v];
-                if (fv & HYB_FIRST_ENDS) { ended = true; break; }
-            }
-            if (ended) {
-                T* yp = a.y + rs + sOpenRow[w];
-                *yp = axpby(alpha, tot, beta, yp);
+    if (tid == 0) {
+        const bool head = (int)sOff[0] < 0;                              // the tile starts inside row rs (split row)
+        T    running = T(0);
+        bool any_end = false;
+#pragma unroll
+        for (int w = 0; w < SEG_WARPS; w++) {
+            const int fr = sFirstRow[w];
+            if (fr >= 0) {
+                const T tot = running + sFirst[w];
+                if (fr == 0 && head) a.plan.head_part[b] = (double)tot;
+                else { T* yp = a.y + rs + fr; *yp = axpby(alpha, tot, beta, yp); }
+                running = sOpen[w];
+                any_end = true;
             } else {
-                a.plan.tail_part[b] = (double)tot;             // only the tile's last row can stay open: split row
+                running += sFirst[w];
             }
         }
-        if (w == 0 && (f & HYB_HAS_FIRST)) {                   // the tile starts inside row rs: split row
-            T tot = sFirst[0];
-            if (!(f & HYB_FIRST_ENDS))
-                for (int v = 1; v < 8; v++) {
-                    const int fv = sFlags[v];
-                    if (!(fv & HYB_HAS_FIRST)) break;
-                    tot += sFirst[v];
-                    if (fv & HYB_FIRST_ENDS) break;
-                }
-            a.plan.head_part[b] = (double)tot;
-        }
+        if (head && !any_end) a.plan.head_part[b] = (double)running;    // the whole tile lies inside row rs
+        else if (re < a.rows && cnt > (int)sOff[nr]) a.plan.tail_part[b] = (double)running;   // the tile ends inside row re
     }
 }
 
@@ -682,30 +758,33 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_TILE_MIN_CTAS) csr_hyb_kernel(
 // CTA waits for one atomic round trip; the extra launch costs ~4 us.)
 template <typename T>
 __global__ void __launch_bounds__(256) csr_fixup_kernel(const CsrArgs<T> a) {
-    // Launched with programmatic stream serialization: these 16 CTAs may become resident while the tile kernel is
-    // still running (it triggers early), so the launch latency is hidden; they wait here until the tile kernel's
-    // memory is complete and visible.
+    // When launched with programmatic stream serialization (opt-in) these 16 CTAs may become resident while the tile
+    // kernel is still running; they wait here until its memory is complete and visible.  No-op in plain stream order.
     cudaGridDependencySynchronize();
     sum_split_rows<T>(a, a.s.a(), a.s.b(), /*whole_grid=*/true);
 }
 
+// Plain stream order by default.  B200SPMV_PDL=1 opts into programmatic stream serialization (the fix-up CTAs become
+// resident while the tile kernel drains; ~0.5 us on a 100 us call).  It is opt-in because one 4-GPU run next to NCCL
+// kernels hung in round 1 and the cause was never established (profiles/README.md).
 template <typename T>
-static void launch_fixup(const CsrArgs<T>& a, cudaStream_t stream) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(16);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const char* no_pdl = getenv("B200SPMV_NO_PDL");            // plain stream order instead (multi-process runs set it)
-    if ((no_pdl && no_pdl[0] == '1') || cudaLaunchKernelEx(&cfg, csr_fixup_kernel<T>, a) != cudaSuccess) {
-        (void)cudaGetLastError();
-        csr_fixup_kernel<T><<<16, 256, 0, stream>>>(a);      // plain stream order is always correct
+static cudaError_t launch_fixup(const CsrArgs<T>& a, cudaStream_t stream) {
+    if (a.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, csr_fixup_kernel<T>, a) == cudaSuccess) return cudaSuccess;
+        (void)cudaGetLastError();                             // the attribute was refused: fall through to plain order
     }
+    csr_fixup_kernel<T><<<16, 256, 0, stream>>>(a);
+    return cudaGetLastError();
 }
 
 
@@ -1162,7 +1241,7 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_RW_MIN_CTAS) csr_rowwise_kerne
     const int2 st = a.plan.tiles[b], en = a.plan.tiles[b + 1];
     const int  rs = st.x, ns = st.y, re = en.x, ne = en.y;
     const T alpha = a.s.a(), beta = a.s.b();
-    cudaTriggerProgrammaticLaunchCompletion();
+    if (a.pdl) cudaTriggerProgrammaticLaunchCompletion();
 
     bool head = false;
     int  head_end = ns;                      // non-zeros [ns, head_end) belong to the split row rs
@@ -1199,13 +1278,15 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_RW_MIN_CTAS) csr_rowwise_kerne
     }
 }
 
-// SMs x resident CTAs per SM of a kernel on the current device (cached per device / kernel).
+// SMs x resident CTAs per SM of a kernel on the current device (cached per device / kernel, thread-safe).
 static int resident_ctas(const void* kernel, int block = CSR_BLOCK, size_t dyn_smem = 0) {
     struct Entry { int dev; const void* k; int n; };
-    static Entry cache[32];
+    static Entry cache[64];
     static int ncache = 0;
+    static std::mutex mu;
     int dev = 0;
     cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
     for (int i = 0; i < ncache; i++)
         if (cache[i].dev == dev && cache[i].k == kernel) return cache[i].n;
     int sms = 148, per = 1;
@@ -1214,7 +1295,7 @@ static int resident_ctas(const void* kernel, int block = CSR_BLOCK, size_t dyn_s
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, block, dyn_smem);
     if (per < 1) per = 1;
     const int n = sms * per;
-    if (ncache < 32) cache[ncache++] = Entry{dev, kernel, n};
+    if (ncache < 64) cache[ncache++] = Entry{dev, kernel, n};
     return n;
 }
 
@@ -1224,6 +1305,7 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
                       const void* x, void* y, void* ws) {
     const int64_t nt = csr_num_tiles(rows, nnz);
     if (nt == 0) return 0;
+    const Config& cf = config();
     CsrArgs<T> a;
     a.off = (const int*)off; a.col = (const int*)col; a.val = (const T*)val;
     a.x = (const T*)x; a.y = (T*)y; a.base = base; a.rows = (int)rows; a.nnz = (int)nnz;
@@ -1233,50 +1315,44 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
     a.trace = nullptr;
     a.num_tiles = (unsigned)nt;
     a.tile_stride = 1;
-    if (const char* e = getenv("B200SPMV_TILE_ORDER")) {
-        if (!strcmp(e, "scatter") && nt > 2) {        // stride ~ 0.618 * nt, coprime with nt -> a permutation of the tiles
-            auto gcd = [](uint64_t x, uint64_t y) { while (y) { uint64_t t = x % y; x = y; y = t; } return x; };
-            uint64_t st = (uint64_t)(0.6180339887 * (double)nt) | 1;
-            while (gcd(st, (uint64_t)nt) != 1) st += 2;
-            a.tile_stride = (unsigned)(st % (uint64_t)nt);
-        }
+    a.seg_dense = cf.seg_dense;
+    a.pdl = cf.pdl;
+    if (cf.tile_scatter && nt > 2) {                  // stride ~ 0.618 * nt, coprime with nt -> a permutation of the tiles
+        auto gcd = [](uint64_t x, uint64_t y) { while (y) { uint64_t t = x % y; x = y; y = t; } return x; };
+        uint64_t st = (uint64_t)(0.6180339887 * (double)nt) | 1;
+        while (gcd(st, (uint64_t)nt) != 1) st += 2;
+        a.tile_stride = (unsigned)(st % (uint64_t)nt);
     }
 #ifdef B200_CSR_TRACE
     a.trace = g_trace_ptr;
 #endif
     // Which kernel?  Measured on B200 (profiles/): matrices with short rows (stencils, < 12 non-zeros per row on
-    // average) run fastest on the persistent software-pipelined kernel; longer / skewed rows on one CTA per tile.
-    // B200SPMV_CSR_KERNEL=tile|pipe|ws|rowwise overrides (experiments), as does -DB200_CSR_KERNEL at build time.
+    // average) run fastest on the persistent software-pipelined kernel; longer / skewed rows on one CTA per tile with
+    // register accumulation (seg).  B200SPMV_CSR_KERNEL=tile|pipe|ws|rowwise|seg (or b200spmv_set_option) overrides,
+    // as does -DB200_CSR_KERNEL at build time.
     int mode = B200_CSR_KERNEL;
-    if (mode < 0) {
-        const char* e = getenv("B200SPMV_CSR_KERNEL");   // read per call (~0.1 us) so tests can switch kernels
-        const int env_mode = !e ? -1 : !strcmp(e, "tile") ? 0 : !strcmp(e, "pipe") ? 1 : !strcmp(e, "ws") ? 2 : !strcmp(e, "rowwise") ? 3 : !strcmp(e, "tile2") ? 4 : !strcmp(e, "hyb") ? 5 : -1;
-        mode = env_mode >= 0 ? env_mode : (nnz >= 12 * rows ? 0 : 1);
-    }
+    if (mode < 0) mode = cf.csr_kernel >= 0 ? cf.csr_kernel : (nnz >= 12 * rows ? 5 : 1);
     if (mode == 2 && (((uintptr_t)col | (uintptr_t)val | (uintptr_t)off) & 15) != 0) mode = 1;   // TMA needs 16 B alignment
-    if (mode == 0) {
-        csr_tile_kernel<T, false><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
-        launch_fixup<T>(a, stream);
-    } else if (mode == 4) {
-        csr_tile_kernel<T, true><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
-        launch_fixup<T>(a, stream);
-    } else if (mode == 5) {
-        csr_hyb_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
-        launch_fixup<T>(a, stream);
-    } else if (mode == 3) {
-        csr_rowwise_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
-        launch_fixup<T>(a, stream);
+    cudaError_t err = cudaSuccess;
+    if (mode == 0 || mode == 3 || mode == 5) {
+        if (mode == 0)      csr_tile_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+        else if (mode == 5) csr_seg_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+        else                csr_rowwise_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
+        err = cudaGetLastError();                      // a failed main launch must not be masked by the fix-up launch
+        if (err == cudaSuccess) err = launch_fixup<T>(a, stream);
     } else if (mode == 2) {
         const size_t dyn = (size_t)WS_STAGES * WsStage<T>::bytes;
         int64_t grid = (int64_t)resident_ctas((const void*)csr_ws_kernel<T>, WS_THREADS, dyn);
         if (grid > nt) grid = nt;
         csr_ws_kernel<T><<<(unsigned)grid, WS_THREADS, dyn, stream>>>(a, (int)nt);
+        err = cudaGetLastError();
     } else {
         int64_t grid = (int64_t)resident_ctas((const void*)csr_pipe_kernel<T>);
         if (grid > nt) grid = nt;
         csr_pipe_kernel<T><<<(unsigned)grid, CSR_BLOCK, 0, stream>>>(a, (int)nt);
+        err = cudaGetLastError();
     }
-    return (int)cudaGetLastError();
+    return (int)err;
 }
 
 }  // namespace b200

@@ -1,4 +1,5 @@
-// workload_gen.cu -- device-side synthetic workload generators (bench / test plumbing, not the hot path).
+// workload_gen.cu -- device-side synthetic workload generators (bench / test plumbing, not the hot path;
+// built into its own libb200gen.so -- the product library libb200spmv.so exports none of this).
 //
 // Bit-identical to the CPU generators in oracle/spmv_oracle.c (same counter hash, same insertion order), so
 // the full-size benchmark matrices never have to cross PCIe and the parity tests can check the integer work
@@ -8,7 +9,7 @@
 //   7-pt stencil . cuDSS/simple_residual/laplace_generator.hxx:34-107
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include "../../include/b200spmv.h"
+#include "../../include/b200gen.h"
 
 namespace b200gen {
 

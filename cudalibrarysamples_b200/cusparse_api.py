@@ -76,6 +76,23 @@ class Api:
             _lib.shim()
             self.lib = C.CDLL(lib_path, mode=C.RTLD_LOCAL)
 
+    # ---- run-time switches / call counters of the product library (include/b200spmv.h) --------------
+    def set_option(self, key: str, value: str) -> None:
+        """b200spmv_set_option: e.g. ("B200SPMV_CSR_KERNEL", "seg" | "tile" | "pipe" | "ws" | "rowwise" | "auto")."""
+        if self.impl != "b200":
+            raise ValueError("options belong to the b200 library")
+        if self.lib.b200spmv_set_option(key.encode(), value.encode()) != 0:
+            raise ValueError(f"unknown option {key}={value}")
+
+    def stats(self) -> dict:
+        """SpMV calls served by our kernels / forwarded to the closed library / CSR analyses run, since the last reset."""
+        n, f, a = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        (self.lib if self.impl == "b200" else _lib.shim()).b200spmv_get_stats(C.byref(n), C.byref(f), C.byref(a))
+        return dict(native=int(n.value), forwarded=int(f.value), analyze=int(a.value))
+
+    def reset_stats(self) -> None:
+        (self.lib if self.impl == "b200" else _lib.shim()).b200spmv_reset_stats()
+
     # ---- helpers ---------------------------------------------------------------------------------
     def _call(self, lib, name, *args):
         st = getattr(lib, name)(*args)

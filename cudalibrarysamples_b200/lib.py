@@ -29,6 +29,7 @@ REAL_CUSPARSE_CANDIDATES = (
 )
 
 _shim = None
+_gen = None
 _real = None
 _real_path = None
 
@@ -82,3 +83,14 @@ def shim(build_if_missing: bool = False) -> C.CDLL:
         lib.b200spmv_version.restype = C.c_char_p
         _shim = lib
     return _shim
+
+
+def gen() -> C.CDLL:
+    """libb200gen.so: device-side synthetic-workload generators (bench / test plumbing, include/b200gen.h)."""
+    global _gen
+    if _gen is None:
+        path = _build.GEN_LIB_PATH
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _gen = C.CDLL(path, mode=C.RTLD_LOCAL)
+    return _gen

@@ -45,7 +45,7 @@ def rmat_scale(n):
 
 def uniform(seed, count, dtype=torch.float64, device="cuda", i0=0):
     out = torch.empty(count, dtype=dtype, device=device)
-    _check(_lib.shim().b200gen_uniform(_stream(), C.c_int(_dt(dtype)), C.c_uint64(seed), C.c_int64(i0), C.c_int64(count),
+    _check(_lib.gen().b200gen_uniform(_stream(), C.c_int(_dt(dtype)), C.c_uint64(seed), C.c_int64(i0), C.c_int64(count),
                                        C.c_void_p(out.data_ptr())), "b200gen_uniform")
     return out
 
@@ -59,7 +59,7 @@ def rmat_csr(rows, cols=None, avg_nnz=16, seed=42, val_seed=43, dtype=torch.floa
     cand = int(math.ceil(target * RMAT_OVERSAMPLE))
     tA, tAB, tABC = rmat_thresholds(abcd)
     keys = torch.empty(cand, dtype=torch.int64, device=device)
-    L = _lib.shim()
+    L = _lib.gen()
     for e0 in range(0, cand, chunk):
         n = min(chunk, cand - e0)
         _check(L.b200gen_rmat_keys(_stream(), C.c_uint64(seed), C.c_int64(e0), C.c_int64(n), C.c_int32(scale), C.c_uint64(tA),
@@ -92,7 +92,7 @@ def rmat_csr(rows, cols=None, avg_nnz=16, seed=42, val_seed=43, dtype=torch.floa
 def stencil5_csr(grid, mass=0.04, ux=0.0, uy=0.0, device="cuda"):
     """cg_example.c:71-128 (defaults) / bicgstab_example.c:69-127 (mass=.3, ux=.3, uy=.2); fp64 like the samples."""
     n = grid * grid
-    L = _lib.shim()
+    L = _lib.gen()
     counts = torch.empty(n, dtype=torch.int32, device=device)
     _check(L.b200gen_stencil5_counts(_stream(), C.c_int32(grid), C.c_void_p(counts.data_ptr())), "stencil5_counts")
     off = torch.zeros(n + 1, dtype=torch.int32, device=device)
@@ -109,7 +109,7 @@ def stencil5_csr(grid, mass=0.04, ux=0.0, uy=0.0, device="cuda"):
 def laplace7_csr(nx, dtype=torch.float64, device="cuda"):
     """cuDSS/simple_residual/laplace_generator.hxx:34-107."""
     n = nx ** 3
-    L = _lib.shim()
+    L = _lib.gen()
     counts = torch.empty(n, dtype=torch.int32, device=device)
     _check(L.b200gen_laplace7_counts(_stream(), C.c_int32(nx), C.c_void_p(counts.data_ptr())), "laplace7_counts")
     off = torch.zeros(n + 1, dtype=torch.int32, device=device)

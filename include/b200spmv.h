@@ -74,17 +74,17 @@ B200SPMV_EXPORT int    b200spmv_sell_mv(void* stream, int dtype, int64_t rows, i
                                         int32_t base, const void* alpha, const void* beta, int scalars_on_device,
                                         const void* x, void* y, void* workspace);
 
-/* Synthetic-workload generators on the device (bench / tests plumbing; bit-identical to oracle/spmv_oracle.c). */
-B200SPMV_EXPORT int b200gen_rmat_keys(void* stream, uint64_t seed, int64_t e0, int64_t count, int32_t scale,
-                                      uint64_t tA, uint64_t tAB, uint64_t tABC, int64_t rows, int64_t cols,
-                                      int64_t* keys_out);
-B200SPMV_EXPORT int b200gen_uniform(void* stream, int dtype, uint64_t seed, int64_t i0, int64_t count, void* out);
-B200SPMV_EXPORT int b200gen_stencil5_counts(void* stream, int32_t grid, int32_t* counts_out);
-B200SPMV_EXPORT int b200gen_stencil5_fill(void* stream, int32_t grid, double mass, double ux, double uy,
-                                          const int32_t* row_offsets, int32_t* col_out, double* val_out);
-B200SPMV_EXPORT int b200gen_laplace7_counts(void* stream, int32_t nx, int32_t* counts_out);
-B200SPMV_EXPORT int b200gen_laplace7_fill(void* stream, int dtype, int32_t nx, const int32_t* row_offsets,
-                                          int32_t* col_out, void* val_out);
+/* Run-time switches (tests / tuning sweeps; never needed by a caller).  The environment variables of the same names
+ * are read ONCE at first use; afterwards only this call changes them.  Not thread-safe against concurrent launches.
+ *   B200SPMV_CSR_KERNEL = auto|tile|pipe|ws|rowwise|seg     B200SPMV_COO_KERNEL = auto|tile|seg
+ *   B200SPMV_TILE_ORDER = scatter|linear   B200SPMV_PDL = 0|1   B200SPMV_SEG_DENSE = <nnz per row>   B200SPMV_SELL_GENERIC = 0|1
+ * returns 0, or -1 for an unknown key / value. */
+B200SPMV_EXPORT int  b200spmv_set_option(const char* key, const char* value);
+/* Call counters of the cuSPARSE-symbol layer: SpMV calls that ran on our kernels, SpMV calls handed to the closed library
+ * (unsupported combination, NULL / misaligned buffer, B200SPMV_FORWARD=1), CSR analyses run.  Tests assert
+ * forwarded == 0 on the hot path. */
+B200SPMV_EXPORT void b200spmv_get_stats(uint64_t* native_calls, uint64_t* forwarded_calls, uint64_t* analyze_calls);
+B200SPMV_EXPORT void b200spmv_reset_stats(void);
 
 B200SPMV_EXPORT const char* b200spmv_version(void);
 

@@ -83,11 +83,23 @@ if os.environ.get("SWEEP_SET") == "final":
     }
 if os.environ.get("SWEEP_SET") == "ab":
     VARIANTS = {k: {} for k in ['t2048_l256', 't1536_l512_occ6', 't1536_l256_occ6', 't2560_l512_occ4', 't1024_l256_b128_occ10', 't3072_l512_b384_occ3']}
+if os.environ.get("SWEEP_SET") == "seg":
+    # csr_seg_kernel: resident CTAs (register cap), batch depth, with / without the staged-product fallback
+    VARIANTS = {}
+    for (o, k, staged) in [(4, 4, 1), (5, 4, 1), (6, 4, 1), (5, 2, 1), (6, 2, 1), (6, 4, 0), (8, 2, 0), (5, 4, 0), (4, 4, 0), (6, 2, 0)]:
+        VARIANTS[f"seg_occ{o}_k{k}_st{staged}"] = dict(SEG=(o, k, staged))
+    VARIANTS["seg_t1024_b128_occ10_k4_st0"] = dict(SEG=(10, 4, 0), TILE=1024, LONG=256, BLOCK=128)
+    VARIANTS["seg_t1024_b256_occ6_k2_st0"] = dict(SEG=(6, 2, 0), TILE=1024, LONG=256, BLOCK=256)
+    VARIANTS["seg_t3072_b384_occ4_k4_st0"] = dict(SEG=(4, 4, 0), TILE=3072, LONG=512, BLOCK=384)
 if os.environ.get("SWEEP_SET") == "ablate":
     VARIANTS = dict(ABL, t2048_b256_k4_occ6=VARIANTS["t2048_b256_k4_occ6"])
 
 
 def flags(v):
+    if "SEG" in v:
+        o, k, staged = v["SEG"]
+        base = dict(TILE=v.get("TILE", 2048), LONG=v.get("LONG", 512), BLOCK=v.get("BLOCK", 256), BATCH=4, MIN=5)
+        return flags(base) + ["-DB200_CSR_KERNEL=5", f"-DB200_SEG_MIN_CTAS={o}", f"-DB200_SEG_BATCH={k}", f"-DB200_SEG_STAGED={staged}"]
     if "ABL" in v:
         return flags({k: x for k, x in v.items() if k != "ABL"}) + [f"-DB200_CSR_ABLATE={v['ABL']}"]
     if "RW" in v:
@@ -113,7 +125,7 @@ def build():
         out = os.path.join(VDIR, f"libb200spmv_{tag}.so")
         b.build_native(extra_flags=flags(v), out_path=out, tag="v_" + tag)
         log = open(os.path.join(ROOT, "cudalibrarysamples_b200", "build", "v_" + tag, "build.log")).read()
-        i = log.find("csr_rowwise_kernelIdEE") if "RW" in v else log.find("csr_ws_kernelIdEE") if "WS" in v else max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
+        i = log.find("csr_seg_kernelIdEE") if "SEG" in v else log.find("csr_rowwise_kernelIdEE") if "RW" in v else log.find("csr_ws_kernelIdEE") if "WS" in v else max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
         regs = log[i:i + 400].split("Used ")[1].split(",")[0] if i >= 0 else "?"
         print(tag, regs)
 
@@ -150,8 +162,8 @@ def run(workloads, variants=None, steps=100):
     results = {}
     libs = [("default", None)] + [(t, os.path.join(VDIR, f"libb200spmv_{t}.so")) for t in VARIANTS if (variants is None or t in variants)]
     libs = [(t, p) for t, p in libs if p is None or os.path.exists(p)]
-    if os.environ.get("SWEEP_SET") == "kernels":     # every CSR kernel of the default library, picked through the env switch
-        libs = [("default", None)] + [("kernel:" + k, None) for k in ("tile", "pipe", "tile2", "hyb", "rowwise", "ws")]
+    if os.environ.get("SWEEP_SET") == "kernels":     # every CSR kernel of the default library, picked through b200spmv_set_option
+        libs = [("default", None)] + [("kernel:" + k, None) for k in ("tile", "pipe", "seg", "seg:1", "seg:8", "seg:16", "seg:48", "rowwise", "ws")]
     for wl in workloads:
         rows, off, col, val = make_workload(wl)
         nnz = int(col.numel())
@@ -160,11 +172,11 @@ def run(workloads, variants=None, steps=100):
         ref = None
         print(f"== {wl}: rows={rows} nnz={nnz} alg_bytes={nbytes / 1e6:.1f} MB", flush=True)
         for tag, path in libs + [("cusparse", "closed")]:
-            if tag.startswith("kernel:"):
-                os.environ["B200SPMV_CSR_KERNEL"] = tag.split(":")[1]
-            else:
-                os.environ.pop("B200SPMV_CSR_KERNEL", None)
             api = cs.Api("cusparse") if tag == "cusparse" else cs.Api("b200", lib_path=path)
+            if tag != "cusparse":
+                parts = tag.split(":") if tag.startswith("kernel:") else ["", "auto"]
+                api.set_option("B200SPMV_CSR_KERNEL", parts[1])
+                api.set_option("B200SPMV_SEG_DENSE", parts[2] if len(parts) > 2 else "24")
             op = cs.SpMVOperator(api, "csr", rows, rows, dict(off=off, col=col, val=val))
             y = torch.zeros(rows, dtype=torch.float64, device="cuda")
             for _ in range(5):

@@ -6,12 +6,18 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "b200spmv.h")
+GEN_HEADER = os.path.join(ROOT, "include", "b200gen.h")
 
 
-def declared_symbols():
-    text = open(HEADER).read()
-    names = re.findall(r"B200SPMV_EXPORT\s+[\w\s\*]+?\b(\w+)\s*\(", text)
+def declared_symbols(header=HEADER, tag="B200SPMV_EXPORT"):
+    text = open(header).read()
+    names = re.findall(tag + r"\s+[\w\s\*]+?\b(\w+)\s*\(", text)
     return sorted(set(names))
+
+
+def exported(lib):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", lib], text=True)
+    return {line.split()[-1] for line in out.splitlines() if " T " in line}
 
 
 def test_header_declares_the_reference_entry_points():
@@ -25,10 +31,36 @@ def test_header_declares_the_reference_entry_points():
 
 
 def test_library_exports_every_declared_symbol(built_lib):
-    out = subprocess.check_output(["nm", "-D", "--defined-only", built_lib], text=True)
-    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
-    missing = [n for n in declared_symbols() if n not in exported]
+    have = exported(built_lib)
+    missing = [n for n in declared_symbols() if n not in have]
     assert not missing, missing
+
+
+def test_bench_plumbing_is_not_part_of_the_product_abi(built_lib):
+    """The synthetic-workload generators live in libb200gen.so (include/b200gen.h); libb200spmv.so exports none of them."""
+    from cudalibrarysamples_b200 import build
+    assert not [n for n in exported(built_lib) if n.startswith("b200gen")]
+    assert not [n for n in declared_symbols() if n.startswith("b200gen")]
+    gen = declared_symbols(GEN_HEADER, "B200GEN_EXPORT")
+    assert len(gen) >= 6
+    have = exported(build.GEN_LIB_PATH)
+    assert not [n for n in gen if n not in have]
+
+
+def test_options_are_set_through_the_abi_not_the_environment(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    assert lib.b200spmv_set_option(b"B200SPMV_CSR_KERNEL", b"seg") == 0
+    assert lib.b200spmv_set_option(b"B200SPMV_CSR_KERNEL", b"auto") == 0
+    assert lib.b200spmv_set_option(b"B200SPMV_CSR_KERNEL", b"no-such-kernel") == -1
+    assert lib.b200spmv_set_option(b"NO_SUCH_KEY", b"1") == -1
+    n, f, a = ctypes.c_uint64(7), ctypes.c_uint64(7), ctypes.c_uint64(7)
+    lib.b200spmv_reset_stats()
+    lib.b200spmv_get_stats(ctypes.byref(n), ctypes.byref(f), ctypes.byref(a))
+    assert (n.value, f.value, a.value) == (0, 0, 0)
+    # no getenv on the launch path: the only getenv calls of the library sit in the once-only initialisers
+    src = os.path.join(ROOT, "cudalibrarysamples_b200", "csrc")
+    for name in ("spmv_csr.cu", "spmv_coo_sell.cu"):
+        assert "getenv(" not in open(os.path.join(src, name)).read(), name
 
 
 def test_library_loads_without_a_gpu(built_lib):
@@ -49,16 +81,31 @@ def test_library_loads_without_a_gpu(built_lib):
                                None, None, 0, None, None, None) == -1
 
 
-def test_sass_is_sm100a_and_streams_with_128bit_loads(built_lib):
+def kernel_sass(built_lib, pattern):
     sass = subprocess.check_output(["cuobjdump", "-sass", built_lib], text=True)
     assert "sm_100a" in sass or "SM100" in sass.upper()
-    m = re.search(r"Function : \S*csr_pipe_kernelId.*?(?=Function :|\Z)", sass, re.S)
-    assert m, "fp64 CSR kernel not found in the cubin"
-    body = m.group(0)
-    assert re.search(r"LDG\.E\.NA\.64", body)    # L1 no-allocate streaming loads of val[] (coalesced: 256 B per warp)
+    m = re.search(r"Function : \S*" + pattern + r".*?(?=Function :|\Z)", sass, re.S)
+    assert m, pattern + " not found in the cubin"
+    return m.group(0)
+
+
+def test_sass_of_the_default_fp64_csr_kernel(built_lib):
+    """What the default kernel for >= 12 nnz/row (csr_seg_kernel<double>) really emits: 64-bit L1-no-allocate streaming
+    loads of val[] (lane-consecutive: 256 B per warp instruction -- per-lane 128-bit loads were measured slower, see
+    DESIGN.md), 32-bit ones of col_ind[], x through the read-only path, shuffle / vote / redux based row reduction, no
+    tensor cores.  profiles/sass_summary_r2.md holds the per-kernel instruction counts."""
+    body = kernel_sass(built_lib, "csr_seg_kernelId")
+    assert re.search(r"LDG\.E\.NA\.64", body)          # val[]: ld.global.nc.L1::no_allocate.f64
+    assert re.search(r"LDG\.E\.NA(?!\.64)", body)      # col_ind[]: 32-bit no-allocate
     assert re.search(r"LDG\.E\.64\.CONSTANT", body)   # x gathered through the read-only L1 path
-    assert "SHFL" in body                 # warp-shuffle row reduction
-    assert "HMMA" not in body and "UTC" not in body   # no tensor cores: HBM-bound gather-reduce
+    assert "SHFL" in body and "VOTE" in body and "REDUX" in body
+    assert not re.search(r"LDG\.E\S*\.128", body)      # no 128-bit per-lane loads in this kernel
+    assert "HMMA" not in body and "UTC" not in body and "UTMA" not in body   # no tensor cores, no tensor-map TMA
+
+
+def test_sass_of_the_tma_fed_variant(built_lib):
+    body = kernel_sass(built_lib, "csr_ws_kernelId")
+    assert "UBLKCP" in body and "SYNCS" in body         # cp.async.bulk + mbarrier
 
 
 def test_reference_samples_bind_spmv_to_the_shim():

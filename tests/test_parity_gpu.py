@@ -49,12 +49,22 @@ def relerr(got, want):
     return np.linalg.norm(got - want) / (n if n > 0 else 1.0)
 
 
-def run(cs, api, fmt, rows, cols, arrays, x, y0, alpha, beta, base=0, preprocess=True):
+def run(cs, api, fmt, rows, cols, arrays, x, y0, alpha, beta, base=0, preprocess=True, expect_forward=False):
+    """One cusparseSpMV through the C ABI.  For the b200 library the call counters must show that OUR kernel served it
+    (b200spmv_get_stats: forwarded == 0) -- a silent hand-over to the closed library would void the parity claim."""
+    before = api.stats() if api.impl == "b200" else None
     op = cs.SpMVOperator(api, fmt, rows, cols, arrays, base=base, preprocess=preprocess)
     y = y0.clone()
     op(x, y, alpha, beta)
     torch.cuda.synchronize()
     op.close()
+    if before is not None:
+        after = api.stats()
+        if expect_forward:
+            assert after["forwarded"] == before["forwarded"] + 1 and after["native"] == before["native"]
+        else:
+            assert after["forwarded"] == before["forwarded"], "the call was forwarded to the closed library"
+            assert after["native"] == before["native"] + 1
     return y
 
 
@@ -180,6 +190,35 @@ def test_csr_without_preprocess_and_buffer_reuse(cs, b200, dtype):
     op.close()
 
 
+def test_plan_is_trusted_only_after_preprocess(cs, b200):
+    """Without cusparseSpMV_preprocess the external buffer is plain scratch (the caller may share it with SpSV / SpMM or
+    get the address back from a caching allocator with other contents): the plan must be rebuilt on every call.  After
+    preprocess the buffer is the caller's promise, and no further analysis runs."""
+    rows = 30000
+    off, col, val, x, y0 = rmat_case(rows, 8, torch.float64, 31)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    want = O.spmv_csr(off, col, val, x, y0, 1.0, 0.0)
+    op = cs.SpMVOperator(b200, "csr", rows, rows, arrays, preprocess=False)
+    a0 = b200.stats()["analyze"]
+    for _ in range(3):
+        op.buffer.fill_(0xA5)                      # somebody else used the scratch buffer in between
+        y = dev(y0)
+        op(dev(x), y, 1.0, 0.0)
+        torch.cuda.synchronize()
+        assert relerr(y.cpu().numpy(), want) < 1e-12
+    assert b200.stats()["analyze"] == a0 + 3
+    op.close()
+    op = cs.SpMVOperator(b200, "csr", rows, rows, arrays, preprocess=True)
+    a1 = b200.stats()["analyze"]
+    for _ in range(3):
+        y = dev(y0)
+        op(dev(x), y, 1.0, 0.0)
+    torch.cuda.synchronize()
+    assert relerr(y.cpu().numpy(), want) < 1e-12
+    assert b200.stats()["analyze"] == a1
+    op.close()
+
+
 def test_csr_in_place_residual_update(cs, b200):
     # cg_example.c:153-160: R = B; R = -A*X + R with y aliased in/out
     off, col, val = O.gen_stencil5(150)
@@ -205,16 +244,24 @@ def test_csr_base_one(cs, b200, closed, dtype):
     assert relerr(got.cpu().numpy(), lib.cpu().numpy()) < TOL[dtype]
 
 
-@pytest.fixture(params=["tile", "pipe", "ws", "rowwise"])
-def csr_kernel(request):
-    """Every CSR kernel variant of the library must give the same answers (B200SPMV_CSR_KERNEL picks one)."""
-    old = os.environ.get("B200SPMV_CSR_KERNEL")
-    os.environ["B200SPMV_CSR_KERNEL"] = request.param
+@pytest.fixture(params=["tile", "pipe", "ws", "rowwise", "seg", "seg:1", "seg:1000000"])
+def csr_kernel(request, b200):
+    """Every CSR kernel variant of the library must give the same answers (b200spmv_set_option picks one).
+    "seg:N" = csr_seg_kernel with the row-sparse threshold N: 1 sends every tile that has non-zeros down the register
+    path (multi-row steps, > 32 row ends per step), 1000000 sends every tile down the staged-product path."""
+    name, _, dense = request.param.partition(":")
+    b200.set_option("B200SPMV_CSR_KERNEL", name)
+    b200.set_option("B200SPMV_SEG_DENSE", dense or "24")
     yield request.param
-    if old is None:
-        os.environ.pop("B200SPMV_CSR_KERNEL", None)
-    else:
-        os.environ["B200SPMV_CSR_KERNEL"] = old
+    b200.set_option("B200SPMV_CSR_KERNEL", "auto")
+    b200.set_option("B200SPMV_SEG_DENSE", "24")
+
+
+@pytest.fixture(params=["tile", "seg"])
+def coo_kernel(request, b200):
+    b200.set_option("B200SPMV_COO_KERNEL", request.param)
+    yield request.param
+    b200.set_option("B200SPMV_COO_KERNEL", "auto")
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
@@ -237,7 +284,8 @@ def test_every_csr_kernel_variant(cs, b200, csr_kernel, dtype):
     assert relerr(got.cpu().numpy(), O.spmv_csr(off, col, val, xs, ys, 0.75, 0.5)) < 1e-12
 
 
-@pytest.mark.parametrize("name", ["single_huge_row", "huge_then_tiny", "alternating", "all_empty", "trailing_empty"])
+@pytest.mark.parametrize("name", ["single_huge_row", "huge_then_tiny", "alternating", "all_empty", "trailing_empty", "leading_empty",
+                                  "rmat_like_block", "many_rows_end_in_one_step", "rows_of_32", "tile_sized_rows", "exactly_long"])
 def test_every_csr_kernel_variant_edge_profiles(cs, b200, csr_kernel, name):
     lens = EDGE[name]
     rows, cols = lens.size, 120000
@@ -289,6 +337,10 @@ EDGE = {
     "one_by_one": np.array([1]),
     "trailing_empty": np.concatenate([np.full(10, 40), np.zeros(9000, int)]),
     "leading_empty": np.concatenate([np.zeros(9000, int), np.full(10, 40)]),
+    "rmat_like_block": np.tile([500, 158, 158, 50, 158, 50, 50, 16, 158, 50, 50, 16, 50, 16, 16, 5], 12),
+    "many_rows_end_in_one_step": np.concatenate([[1800], np.ones(40, int), np.zeros(50, int), np.full(30, 2), [1900, 0, 0, 0, 1, 1, 1],
+                                                 [2500], np.zeros(40, int), [1500], np.zeros(70, int), [30, 2000]]),
+    "rows_of_32": np.full(300, 32),
 }
 
 
@@ -364,7 +416,7 @@ def test_unsupported_combinations_are_forwarded_not_broken(cs, b200, closed):
     rows = 5000
     off, col, val, x, y0 = rmat_case(rows, 8, torch.float64, 71)
     arrays = dict(off=dev(off.astype(np.int64)), col=dev(col.astype(np.int64)), val=dev(val))
-    got = run(cs, b200, "csr", rows, rows, arrays, dev(x), dev(y0), 1.0, 0.0)
+    got = run(cs, b200, "csr", rows, rows, arrays, dev(x), dev(y0), 1.0, 0.0, expect_forward=True)
     assert relerr(got.cpu().numpy(), O.spmv_csr(off, col, val, x)) < 1e-12
 
 
@@ -384,7 +436,7 @@ def test_shape_mismatch_is_an_error(cs, b200):
 # ------------------------------------------------------------------------------------------ COO / SELL
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (-1.0, 1.0)])
-def test_coo_vs_oracle_and_cusparse(cs, b200, closed, dtype, alpha, beta):
+def test_coo_vs_oracle_and_cusparse(cs, b200, closed, coo_kernel, dtype, alpha, beta):
     rows = 40000
     off, col, val, x, y0 = rmat_case(rows, 16, dtype, 81)
     row = O.csr_to_coo_rows(off)
@@ -396,7 +448,7 @@ def test_coo_vs_oracle_and_cusparse(cs, b200, closed, dtype, alpha, beta):
     assert relerr(got, lib) < TOL[dtype]
 
 
-def test_coo_unsorted_and_tiny(cs, b200):
+def test_coo_unsorted_and_tiny(cs, b200, coo_kernel):
     rows = 3000
     off, col, val, x, y0 = rmat_case(rows, 8, torch.float64, 91)
     row = O.csr_to_coo_rows(off)
