@@ -182,40 +182,43 @@ __global__ void __launch_bounds__(COO_BLOCK, B200_COO_SEG_MIN_CTAS) coo_seg_kern
         }
     };
     issue(0);
-#pragma unroll
+    // run-time loops over the steps (only the load / gather loops of a batch are unrolled): one copy of the flush code
+    // keeps the kernel inside the instruction cache (the fully unrolled version was 47 KB of SASS)
+#pragma unroll 1
     for (int kb = 0; kb < COO_SEG_STEPS; kb += COO_SEG_BATCH) {
-        if (n0 + kb * 32 < n1) {                              // warp-uniform
-            T   p[COO_SEG_BATCH];
-            int rr[COO_SEG_BATCH];
-            unsigned mm[COO_SEG_BATCH];
+        if (n0 + kb * 32 >= n1) break;                        // warp-uniform
+        T   p[COO_SEG_BATCH];
+        int rr[COO_SEG_BATCH];
+        unsigned mm[COO_SEG_BATCH];
 #pragma unroll
-            for (int k = 0; k < COO_SEG_BATCH; k++) {
-                const bool live = n0 + (kb + k) * 32 + lane < n1;
-                p[k]  = live ? v[k] * __ldg(a.x + (c[k] - a.base)) : T(0);
-                rr[k] = r[k];
-                mm[k] = __ballot_sync(0xffffffffu, live && r[k] != rn[k]);
-            }
-            if (kb + COO_SEG_BATCH < COO_SEG_STEPS && n0 + (kb + COO_SEG_BATCH) * 32 < n1) issue(kb + COO_SEG_BATCH);
+        for (int k = 0; k < COO_SEG_BATCH; k++) {
+            const bool live = n0 + (kb + k) * 32 + lane < n1;
+            p[k]  = live ? v[k] * __ldg(a.x + (c[k] - a.base)) : T(0);
+            rr[k] = r[k];
+            mm[k] = __ballot_sync(0xffffffffu, live && r[k] != rn[k]);
+        }
+        if (kb + COO_SEG_BATCH < COO_SEG_STEPS && n0 + (kb + COO_SEG_BATCH) * 32 < n1) issue(kb + COO_SEG_BATCH);
+#pragma unroll 1
+        for (int k = 0; k < COO_SEG_BATCH; k++) {
+            T pk = p[0]; int rk = rr[0]; unsigned m = mm[0];  // [k] with a run-time k: select chains, not local memory
 #pragma unroll
-            for (int k = 0; k < COO_SEG_BATCH; k++) {
-                const unsigned m = mm[k];
-                if (m == 0u) { acc += p[k]; continue; }       // the whole step lies inside one run
-                const int e1 = __ffs(m) - 1, ek = 31 - __clz(m);
-                const T t1 = coo_warp_allsum(acc + (lane <= e1 ? p[k] : T(0)));
-                T q = (lane > e1 && lane <= ek) ? p[k] : T(0);
-                if (m & (m - 1u)) {                           // more runs end: segmented inclusive scan
-                    const unsigned below = m & ((1u << lane) - 1u);
-                    const int dist = (lane > e1 && lane <= ek) ? lane - (32 - __clz(below)) : 0;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        if (__ballot_sync(0xffffffffu, dist >= d) == 0u) break;
-                        const T t = __shfl_up_sync(0xffffffffu, q, d);
-                        if (dist >= d) q += t;
-                    }
+            for (int j = 1; j < COO_SEG_BATCH; j++) { pk = k == j ? p[j] : pk; rk = k == j ? rr[j] : rk; m = k == j ? mm[j] : m; }
+            if (m == 0u) { acc += pk; continue; }             // the whole step lies inside one run
+            const int e1 = __ffs(m) - 1, ek = 31 - __clz(m);
+            const T t1 = coo_warp_allsum(acc + (lane <= e1 ? pk : T(0)));
+            T q = (lane > e1 && lane <= ek) ? pk : T(0);
+            if (m & (m - 1u)) {                               // more runs end: segmented inclusive scan
+                const unsigned below = m & ((1u << lane) - 1u);
+                const int dist = (lane > e1 && lane <= ek) ? lane - (32 - __clz(below)) : 0;
+#pragma unroll 1
+                for (int d = 1; d < 32; d <<= 1) {
+                    if (__ballot_sync(0xffffffffu, dist >= d) == 0u) break;
+                    const T t = __shfl_up_sync(0xffffffffu, q, d);
+                    if (dist >= d) q += t;
                 }
-                if ((m >> lane) & 1u) atomicAdd(a.y + (rr[k] - a.base), alpha * (lane == e1 ? t1 : q));
-                acc = lane > ek ? p[k] : T(0);
             }
+            if ((m >> lane) & 1u) atomicAdd(a.y + (rk - a.base), alpha * (lane == e1 ? t1 : q));
+            acc = lane > ek ? pk : T(0);
         }
     }
 }

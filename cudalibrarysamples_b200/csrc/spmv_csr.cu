@@ -634,91 +634,91 @@ __global__ void __launch_bounds__(CSR_BLOCK, B200_SEG_MIN_CTAS) csr_seg_kernel(c
         v[k] = live ? ldg_stream(valp + e) : T(0);
     }
 
+    // Run-time loops on purpose (no unrolling over the steps): fully unrolled, the flush code below was instantiated 12
+    // times, the kernel was 159 KB of SASS and "no instruction" (instruction-cache misses) was its top stall reason
+    // (profiles/ncu_r2_seg_v1_icache.md: 176 us).  Only the short load / gather loops over a batch are unrolled.
+#pragma unroll 1
+    for (int kb = 0; kb < steps_w; kb += SEG_BATCH) {                    // block-uniform trip count
+        T p[SEG_BATCH];
 #pragma unroll
-    for (int kb = 0; kb < SEG_WSTEPS; kb += SEG_BATCH) {
-        if (kb < steps_w) {                                              // block-uniform
-            T p[SEG_BATCH];
+        for (int k = 0; k < SEG_BATCH; k++) {
+            const int e = (s0 + kb + k) * 32 + lane;
+            const bool live = kb + k < steps_w && e >= lead && e < span;
+            p[k] = live ? v[k] * __ldg(a.x + (c[k] - a.base)) : T(0);
+        }
+        if (kb + SEG_BATCH < steps_w) {                                  // next batch of the stream (block-uniform)
 #pragma unroll
             for (int k = 0; k < SEG_BATCH; k++) {
-                const int e = (s0 + kb + k) * 32 + lane;
-                const bool live = kb + k < steps_w && e >= lead && e < span;
-                p[k] = live ? v[k] * __ldg(a.x + (c[k] - a.base)) : T(0);
+                const int e = (s0 + kb + SEG_BATCH + k) * 32 + lane;
+                const bool live = kb + SEG_BATCH + k < steps_w && e >= lead && e < span;
+                c[k] = live ? ldg_stream(colp + e) : a.base;
+                v[k] = live ? ldg_stream(valp + e) : T(0);
             }
-            if (kb + SEG_BATCH < SEG_WSTEPS && kb + SEG_BATCH < steps_w) {   // next batch of the stream (block-uniform)
-#pragma unroll
-                for (int k = 0; k < SEG_BATCH; k++) {
-                    const int e = (s0 + kb + SEG_BATCH + k) * 32 + lane;
-                    const bool live = kb + SEG_BATCH + k < steps_w && e >= lead && e < span;
-                    c[k] = live ? ldg_stream(colp + e) : a.base;
-                    v[k] = live ? ldg_stream(valp + e) : T(0);
-                }
-            }
-            if (kb == 0) {
-                __syncthreads();                                         // sOff is staged; the loads above are in flight
-                if (active) {
-                    // rows whose end lies at or before the chunk start were finished by earlier warps (warp 0: none)
-                    cur = warp == 0 ? 0 : warp_count_ended(sOff, nr, cs, lane);
-                    ws = (int)sOff[cur + lane];
-                    we = (int)sOff[cur + lane + 1];
-                }
-            }
+        }
+        if (kb == 0) {
+            __syncthreads();                                             // sOff is staged; the loads above are in flight
             if (active) {
+                // rows whose end lies at or before the chunk start were finished by earlier warps (warp 0: none)
+                cur = warp == 0 ? 0 : warp_count_ended(sOff, nr, cs, lane);
+                ws = (int)sOff[cur + lane];
+                we = (int)sOff[cur + lane + 1];
+            }
+        }
+        if (!active) continue;
+#pragma unroll 1
+        for (int k = 0; k < SEG_BATCH; k++) {
+            const int sb = (s0 + kb + k) * 32 - lead;                    // tile-relative position of lane 0
+            if (kb + k >= steps_w || sb >= ce) break;                    // warp-uniform (the last warp's chunk may end early)
+            const int step_end = min(sb + 32, ce);
+            T pend = p[0];                                               // p[k] with a run-time k: a select chain, not local memory
 #pragma unroll
-                for (int k = 0; k < SEG_BATCH; k++) {
-                    if (kb + k < steps_w) {                              // block-uniform
-                        const int sb = (s0 + kb + k) * 32 - lead;        // tile-relative position of lane 0
-                        if (sb < ce) {                                   // warp-uniform (the last warp's chunk may end early)
-                            const int step_end = min(sb + 32, ce);
-                            T pend = p[k];
-                            for (;;) {
-                                const int kk = __popc(__ballot_sync(0xffffffffu, we <= step_end));   // rows ending in this step
-                                if (kk == 0) break;
-                                const bool has = lane < kk && we > max(ws, cs);      // row cur + lane has elements in this chunk
-                                const unsigned m = __reduce_or_sync(0xffffffffu, has ? 1u << (we - 1 - sb) : 0u);
-                                T res = T(0);
-                                if (m != 0u) {
-                                    const int e1 = __ffs(m) - 1, ek = 31 - __clz(m);
-                                    const T t1 = warp_allsum(acc + (lane <= e1 ? pend : T(0)));
-                                    T q = (lane > e1 && lane <= ek) ? pend : T(0);
-                                    if (m & (m - 1u)) {                              // more rows end: segmented inclusive scan
-                                        const unsigned below = m & ((1u << lane) - 1u);
-                                        const int dist = (lane > e1 && lane <= ek) ? lane - (32 - __clz(below)) : 0;   // lanes before me in my segment
-#pragma unroll
-                                        for (int d = 1; d < 32; d <<= 1) {
-                                            if (__ballot_sync(0xffffffffu, dist >= d) == 0u) break;      // no segment that long
-                                            const T t = __shfl_up_sync(0xffffffffu, q, d);
-                                            if (dist >= d) q += t;
-                                        }
-                                    }
-                                    res = lane == e1 ? t1 : q;
-                                    acc = T(0);
-                                    acc_live = false;
-                                    pend = lane > ek ? pend : T(0);
-                                }
-                                T val = __shfl_sync(0xffffffffu, res, has ? we - 1 - sb : 0);
-                                val = has ? val : T(0);
-                                if (frow < 0) {                          // the chunk's first row end goes to the stitcher
-                                    first = val;                         // lane 0 keeps it (only lane 0 stores it)
-                                    frow = cur;
-                                    if (lane > 0 && lane < kk) {
-                                        T* yp = a.y + rs + cur + lane;
-                                        *yp = axpby(alpha, val, beta, yp);
-                                    }
-                                } else if (lane < kk) {
-                                    T* yp = a.y + rs + cur + lane;
-                                    *yp = axpby(alpha, val, beta, yp);
-                                }
-                                cur += kk;
-                                ws = (int)sOff[cur + lane];
-                                we = (int)sOff[cur + lane + 1];
-                                if (kk < 32) break;
-                            }
-                            acc += pend;
-                            acc_live = acc_live || __ballot_sync(0xffffffffu, pend != T(0)) != 0u;
+            for (int j = 1; j < SEG_BATCH; j++) pend = k == j ? p[j] : pend;
+#pragma unroll 1
+            for (;;) {
+                const int kk = __popc(__ballot_sync(0xffffffffu, we <= step_end));   // rows ending in this step
+                if (kk == 0) break;
+                const bool has = lane < kk && we > max(ws, cs);          // row cur + lane has elements in this chunk
+                const unsigned m = __reduce_or_sync(0xffffffffu, has ? 1u << (we - 1 - sb) : 0u);
+                T res = T(0);
+                if (m != 0u) {
+                    const int e1 = __ffs(m) - 1, ek = 31 - __clz(m);
+                    const T t1 = warp_allsum(acc + (lane <= e1 ? pend : T(0)));
+                    T q = (lane > e1 && lane <= ek) ? pend : T(0);
+                    if (m & (m - 1u)) {                                  // more rows end: segmented inclusive scan
+                        const unsigned below = m & ((1u << lane) - 1u);
+                        const int dist = (lane > e1 && lane <= ek) ? lane - (32 - __clz(below)) : 0;   // lanes before me in my segment
+#pragma unroll 1
+                        for (int d = 1; d < 32; d <<= 1) {
+                            if (__ballot_sync(0xffffffffu, dist >= d) == 0u) break;          // no segment that long
+                            const T t = __shfl_up_sync(0xffffffffu, q, d);
+                            if (dist >= d) q += t;
                         }
                     }
+                    res = lane == e1 ? t1 : q;
+                    acc = T(0);
+                    acc_live = false;
+                    pend = lane > ek ? pend : T(0);
                 }
+                T val = __shfl_sync(0xffffffffu, res, has ? we - 1 - sb : 0);
+                val = has ? val : T(0);
+                if (frow < 0) {                                          // the chunk's first row end goes to the stitcher
+                    first = val;                                         // lane 0 keeps it (only lane 0 stores it)
+                    frow = cur;
+                    if (lane > 0 && lane < kk) {
+                        T* yp = a.y + rs + cur + lane;
+                        *yp = axpby(alpha, val, beta, yp);
+                    }
+                } else if (lane < kk) {
+                    T* yp = a.y + rs + cur + lane;
+                    *yp = axpby(alpha, val, beta, yp);
+                }
+                cur += kk;
+                ws = (int)sOff[cur + lane];
+                we = (int)sOff[cur + lane + 1];
+                if (kk < 32) break;
             }
+            acc += pend;
+            acc_live = acc_live || __ballot_sync(0xffffffffu, pend != T(0)) != 0u;
         }
     }
     {

@@ -84,12 +84,15 @@ if os.environ.get("SWEEP_SET") == "final":
 if os.environ.get("SWEEP_SET") == "ab":
     VARIANTS = {k: {} for k in ['t2048_l256', 't1536_l512_occ6', 't1536_l256_occ6', 't2560_l512_occ4', 't1024_l256_b128_occ10', 't3072_l512_b384_occ3']}
 if os.environ.get("SWEEP_SET") == "seg":
-    # csr_seg_kernel: resident CTAs (register cap), batch depth, with / without the staged-product fallback
+    # csr_seg_kernel: tile size, resident CTAs (register cap), batch depth, with / without the staged-product fallback
     VARIANTS = {}
     for (o, k, staged) in [(4, 4, 1), (5, 4, 1), (6, 4, 1), (5, 2, 1), (6, 2, 1), (6, 4, 0), (8, 2, 0), (5, 4, 0), (4, 4, 0), (6, 2, 0)]:
         VARIANTS[f"seg_occ{o}_k{k}_st{staged}"] = dict(SEG=(o, k, staged))
+    for (o, k, staged) in [(5, 4, 1), (6, 2, 1), (8, 2, 1), (6, 4, 0), (6, 2, 0), (8, 2, 0), (8, 4, 0)]:
+        VARIANTS[f"seg_t1024_b256_occ{o}_k{k}_st{staged}"] = dict(SEG=(o, k, staged), TILE=1024, LONG=256, BLOCK=256)
     VARIANTS["seg_t1024_b128_occ10_k4_st0"] = dict(SEG=(10, 4, 0), TILE=1024, LONG=256, BLOCK=128)
-    VARIANTS["seg_t1024_b256_occ6_k2_st0"] = dict(SEG=(6, 2, 0), TILE=1024, LONG=256, BLOCK=256)
+    VARIANTS["seg_t1024_b128_occ12_k4_st1"] = dict(SEG=(12, 4, 1), TILE=1024, LONG=256, BLOCK=128)
+    VARIANTS["seg_t512_b128_occ12_k2_st0"] = dict(SEG=(12, 2, 0), TILE=512, LONG=128, BLOCK=128)
     VARIANTS["seg_t3072_b384_occ4_k4_st0"] = dict(SEG=(4, 4, 0), TILE=3072, LONG=512, BLOCK=384)
 if os.environ.get("SWEEP_SET") == "ablate":
     VARIANTS = dict(ABL, t2048_b256_k4_occ6=VARIANTS["t2048_b256_k4_occ6"])
