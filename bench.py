@@ -1,23 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json's metric: fp64 CSR SpMV effective HBM GB/s (and fraction of the HBM roofline).
+"""bench.py -- BASELINE.json's metric: fp64 CSR SpMV effective HBM GB/s (and fraction of the HBM roofline) at 1/2/4/8
+B200, plus CG iterations/s (BASELINE.json configs[3]) as an extra key of the same JSON line.
 
   python bench.py [--gpus N --steps K --warmup W]          our arm: sm_100a kernels through the cuSPARSE C ABI
   python bench.py --impl reference [...]                    reference arm: the samples' host loop on the CPU cores
-  torchrun --nproc-per-node N bench.py --gpus N ...         N>1: row-block shards + one NCCL all-gather of x per step
+  torchrun --nproc-per-node N bench.py --gpus N ...         N>1: row-block shards, x exchanged over NVLink every step
 
 A "step" is one y = A*x (alpha=1, beta=0) over the whole matrix.  Workload at N=1 = BASELINE.json configs[1]:
 R-MAT 1,000,000 x 1,000,000, 16 non-zeros/row on average, fp64 values, int32 indices.  At N>1 the
 matrix grows with N (N*1M rows, "weak" scaling): every rank keeps ~16M non-zeros and receives the other ranks' x.
 Timing: CUDA events on the launching stream around exactly K steps, barrier + synchronize on both sides, max over
 ranks.  No L2 flush: one step streams 212 MB (> 126 MB L2) so val[]/col_ind[] cannot stay resident; x (8 MB) does.
+
+Extra keys of the line (VERDICT r1 "make the measurement contract complete"):
+  north_star_10m    the north-star acceptance config (R-MAT 10M x 16, fp64): us, GB/s, fraction of peak, error vs cuSPARSE
+  cg_config4        BASELINE.json configs[3]: CG, 5-pt Poisson 8192^2, 200 iterations, row-sharded over the N GPUs: iterations/s
+  cusparse_toolkit  the closed library of the CUDA 12.9 toolkit (the one the reference samples link), timed by a C harness
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
+import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -30,6 +39,8 @@ METRIC = "csr_spmv_fp64_effective_hbm_bandwidth"
 UNIT = "GB/s"
 ROWS_PER_GPU = 1_000_000
 AVG_NNZ = 16
+CG_GRID = 8192
+CG_ITERS = 200
 
 
 def csr_bytes(rows, cols, nnz, vb=8, ib=4):
@@ -45,6 +56,17 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_source_sha():
+    """Hash of the kernel sources: profiles/traffic.json is only quoted when it was captured from THIS code."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "cudalibrarysamples_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".cpp", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -111,63 +133,72 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the samples' host verification loop (spmv_csr_op_example.c:307-318) on the host cores
 # ------------------------------------------------------------------------------------------------------------------
-def pick_threads(off, col, val, x):
-    """Host threads for the CPU arm: the fastest of {allowed CPUs, half of them (physical cores), 32}, probed with two
-    repetitions each -- omp_get_max_threads() counts SMT siblings / CPUs outside the cgroup on some boxes and the loop
-    then runs 20x slower."""
-    from oracle import oracle as O
+def host_threads():
+    """Threads for the CPU arm, FIXED per box: the CPUs this process may run on, capped by the cgroup CPU quota
+    (omp_get_max_threads() counts CPUs outside the quota on some boxes: 128 threads on a 64-CPU allocation ran 20x
+    slower in round 1).  No per-run probing: the same count is used by the reference arm and by cpu_baseline."""
     try:
-        allowed = len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        allowed = O.max_threads()
-    cands = sorted({max(1, min(allowed, O.max_threads())), max(1, allowed // 2), max(1, min(32, allowed))}, reverse=True)
-    best_t, best = cands[0], float("inf")
-    for t in cands:
-        sec, _, _ = O.time_csr_f64(off, col, val, x, t, reps=2)
-        if sec < best:
-            best_t, best = t, sec
-    return best_t
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = int(q) / int(p)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    if quota:
+        n = min(n, max(1, int(quota)))
+    return max(1, min(n, 64))          # the loop is memory-bound: beyond 64 threads nothing is gained on these hosts
 
 
-def cpu_reference(off, col, val, x, reps):
+def cpu_times(off, col, val, x, threads, reps):
+    """Per-repetition wall times of the oracle's CSR loop; statistic everywhere = MEDIAN."""
     from oracle import oracle as O
-    threads = pick_threads(off, col, val, x)
-    rows = off.size - 1
-    best, times, _ = O.time_csr_f64(off, col, val, x, threads, reps=reps)
-    gbs = csr_bytes(rows, x.size, col.size) / best / 1e9
-    return gbs, threads, best, times
+    _, times, y = O.time_csr_f64(off, col, val, x, threads, reps=reps)
+    ts = sorted(times)
+    return ts[len(ts) // 2], times, y
 
 
 def run_reference_arm(args):
-    """The reference's own CPU implementation of the path, all host threads, same metric / unit / config."""
+    """The reference's own CPU implementation of the path (the samples' host loop, restated in oracle/spmv_oracle.c),
+    all host threads, same metric / unit / config as our arm: at --gpus N the N*1M-row matrix."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import numpy as np
     from oracle import oracle as O
+    rows = ROWS_PER_GPU * args.gpus
     t_gen = time.time()
-    off, col, val = O.rmat_csr(ROWS_PER_GPU, avg_nnz=AVG_NNZ, seed=42, val_seed=43)
-    x = O.uniform(44, ROWS_PER_GPU)
+    off, col, val = O.rmat_csr(rows, avg_nnz=AVG_NNZ, seed=42, val_seed=43)
+    x = O.uniform(44, rows)
     t_gen = time.time() - t_gen
-    threads = pick_threads(off, col, val, x)
-    rows, nnz = off.size - 1, int(col.size)
-    y = np.zeros(rows)
-    for _ in range(args.warmup):
+    threads = host_threads()
+    nnz = int(col.size)
+    steps = max(args.steps, 20)
+    for _ in range(max(args.warmup, 3)):
         O.time_csr_f64(off, col, val, x, threads, reps=1)
-    _, times, _ = O.time_csr_f64(off, col, val, x, threads, reps=args.steps)
-    total = float(sum(times))
-    ms = 1e3 * total / args.steps
-    gbs = csr_bytes(rows, rows, nnz) / (total / args.steps) / 1e9
-    sample = (f"one full y=A*x per step on the 1,000,000-row R-MAT shard (nnz={nnz}); OpenMP dynamic row chunks, "
-              f"{threads} threads; matrix generated on the CPU in {t_gen:.0f} s (not timed)")
+    med, times, _ = cpu_times(off, col, val, x, threads, steps)
+    gbs = csr_bytes(rows, rows, nnz) / med / 1e9
+    sample = (f"one full y=A*x per step on the {rows}-row R-MAT matrix (nnz={nnz}); OpenMP dynamic row chunks, {threads} threads "
+              f"(fixed: allowed CPUs capped by the cgroup quota and 64); {steps} timed steps, MEDIAN reported "
+              f"(min {min(times) * 1e3:.2f} ms, max {max(times) * 1e3:.2f} ms); matrix generated on the CPU in {t_gen:.0f} s (not timed)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(med * 1e3, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, rows, nnz) | {"reference_arm": "CPU host loop (spmv_csr_op_example.c:307-318 restated, oracle/spmv_oracle.c); per-rank shard size"},
-        "cpu_baseline": {"value": round(gbs, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args.gpus, rows, nnz),
+        "cpu_baseline": {"value": round(gbs, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "statistic": "median"},
         "e2e": {"value": round(gbs, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gflops": round(2 * nnz / (total / args.steps) / 1e9, 3),
+        "gflops": round(2 * nnz / med / 1e9, 3),
+        "reference_arm": "CPU host loop (spmv_csr_op_example.c:307-318 restated, oracle/spmv_oracle.c)",
     }
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
@@ -178,7 +209,7 @@ def workload_config(n_gpus, rows, nnz):
                     "(a,b,c,d)=(0.57,0.19,0.19,0.05), seed 42, duplicates merged, columns sorted, val,x~U(-1,1), int32 indices",
         "baseline_config": "BASELINE.json configs[1] (R-MAT 1M x 1M avg 16 nnz/row, single B200); N>1 grows the matrix to N*1M rows",
         "rows": rows, "cols": rows, "nnz": nnz, "alpha": 1.0, "beta": 0.0,
-        "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} row-block shards of A and y (nnz-balanced), x in equal blocks, one NCCL all-gather of x per step",
+        "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} row-block shards of A and y (nnz-balanced), x in equal blocks, exchanged over NVLink every step",
         "l2": "no flush: 212 MB streamed per step per GPU > 126 MB L2; x stays L2-resident by design",
     }
 
@@ -204,7 +235,9 @@ def prebuilt_spmv_call(cs, op, x, y):
     return call
 
 
-def time_steps(torch, fn, steps, dist_on):
+def time_steps(torch, fn, steps, dist_on, tail=None):
+    """CUDA events on the current stream around `steps` calls of fn; `tail` (optional) makes the current stream wait for
+    side streams before the closing event.  Returns (ms, t0, t1) -- max over ranks when distributed."""
     import torch.distributed as dist
     if dist_on:
         dist.barrier()
@@ -214,6 +247,8 @@ def time_steps(torch, fn, steps, dist_on):
     e0.record()
     for _ in range(steps):
         fn()
+    if tail is not None:
+        tail()
     e1.record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -225,6 +260,154 @@ def time_steps(torch, fn, steps, dist_on):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return ms, t0, t1
+
+
+class PipelinedE2E:
+    """The user-facing call with HOST buffers, every step: pinned host x -> device, cusparseSpMV through the C ABI, device
+    y -> pinned host.  The three legs of consecutive steps overlap (copy streams + two device buffer sets): H2D of step
+    k+1 and D2H of step k-1 run while the kernel of step k does; the SpMV itself stays on the handle's stream."""
+
+    def __init__(self, torch, op, hx, rows, cols):
+        self.torch, self.op = torch, op
+        self.main = torch.cuda.current_stream()
+        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        self.hx = hx
+        self.hy = [torch.empty(rows, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.dx = [torch.empty(cols, dtype=torch.float64, device="cuda") for _ in range(2)]
+        self.dy = [torch.empty(rows, dtype=torch.float64, device="cuda") for _ in range(2)]
+        ev = lambda: [torch.cuda.Event() for _ in range(2)]
+        self.x_ready, self.x_free, self.y_ready, self.y_free = ev(), ev(), ev(), ev()
+        for e in self.x_free + self.y_free:
+            e.record(self.main)
+        self.k = 0
+
+    def step(self):
+        torch, i = self.torch, self.k & 1
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.x_free[i])          # the kernel of step k-2 has finished reading dx[i]
+            self.dx[i].copy_(self.hx, non_blocking=True)
+            self.x_ready[i].record(self.s_in)
+        self.main.wait_event(self.x_ready[i])
+        self.main.wait_event(self.y_free[i])               # the D2H of step k-2 has finished reading dy[i]
+        self.op(self.dx[i], self.dy[i], 1.0, 0.0)
+        self.y_ready[i].record(self.main)
+        self.x_free[i].record(self.main)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.y_ready[i])
+            self.hy[i].copy_(self.dy[i], non_blocking=True)
+            self.y_free[i].record(self.s_out)
+        self.k += 1
+
+    def drain(self):
+        self.main.wait_stream(self.s_out)
+        self.main.wait_stream(self.s_in)
+
+    def last_result(self):
+        return self.hy[(self.k - 1) & 1]
+
+
+def north_star_leg(torch, cs, W, api, peak, steps):
+    """R-MAT 10M x 10M, avg 16 nnz/row, fp64: the north-star acceptance config (target >= 0.70 of HBM peak, error < 1e-12)."""
+    rows = 10_000_000
+    off, col, val = W.rmat_csr(rows, avg_nnz=AVG_NNZ, seed=42, val_seed=43)
+    nnz = int(col.numel())
+    x = W.uniform(44, rows)
+    nbytes = csr_bytes(rows, rows, nnz)
+    out = {"workload": f"R-MAT {rows}x{rows}, nnz={nnz}, fp64, same generator as the headline config", "algorithmic_bytes": nbytes}
+    ys = {}
+    for impl in ("b200", "cusparse"):
+        a = api if impl == "b200" else cs.Api("cusparse")
+        op = cs.SpMVOperator(a, "csr", rows, rows, dict(off=off, col=col, val=val), preprocess=True)
+        y = torch.zeros(rows, dtype=torch.float64, device="cuda")
+        call = prebuilt_spmv_call(cs, op, x, y)
+        for _ in range(5):
+            call()
+        ms, _, _ = time_steps(torch, call, steps, False)
+        us = ms * 1e3 / steps
+        out["ours" if impl == "b200" else "cusparse_torch_bundled"] = {
+            "us_per_spmv": round(us, 2), "value": round(nbytes / us / 1e3, 1), "unit": UNIT, "frac_of_peak": round(nbytes / us / 1e3 / peak, 4)}
+        ys[impl] = y
+        op.close()
+    out["rel_err_vs_cusparse"] = float((torch.linalg.norm(ys["b200"] - ys["cusparse"]) / torch.linalg.norm(ys["cusparse"])).item())
+    out["target"] = {"frac_of_peak": 0.70, "rel_err": 1e-12}
+    return out
+
+
+def cg_leg(torch, dist, cs, W, api, rank, world):
+    """BASELINE.json configs[3]: CG, fp64, 5-pt Poisson 8192^2 (cg_example.c:71-128 generator), 200 fixed iterations,
+    row-sharded over the N GPUs (strong scaling), iterations/s = 200 / max-over-ranks device time."""
+    from cudalibrarysamples_b200.cg import make_cg_solver
+    from cudalibrarysamples_b200.sharded import ShardedCsr
+    n = CG_GRID * CG_GRID
+    if n % world:
+        return {"skipped": f"{n} rows do not divide by {world} ranks"}
+    off, col, val = W.stencil5_csr(CG_GRID)
+    nnz = int(col.numel())
+
+    def make_local(r, c, arrays):
+        return cs.SpMVOperator(api, "csr", r, c, arrays, preprocess=True)
+
+    sh = ShardedCsr(off, col, val, rank, world, make_local, balance="rows")
+    del off, col, val
+    torch.cuda.empty_cache()
+    ones = torch.ones(n, dtype=torch.float64, device="cuda")
+    b = sh.new_y_shard()
+    sh.spmv(sh.new_x_shard(ones), b, alpha=0.75, beta=0.0)      # b = 0.75 * A * 1 (cg_example.c:405-418)
+    del ones
+    solver = make_cg_solver(sh, b)
+    solver.run(3)                                               # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    x, norms = solver.run(CG_ITERS)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    r = b.clone()
+    sh.spmv(x, r, alpha=-1.0, beta=1.0)                         # true residual with one more product (cg_example.c:289-300)
+    rr = torch.dot(r, r).reshape(1)
+    if world > 1:
+        dist.all_reduce(rr)
+    ms = float(ms.item())
+    out = {"metric": "cg_iterations_per_second", "value": round(CG_ITERS / (ms * 1e-3), 2), "unit": "iterations/s",
+           "ms_per_iteration": round(ms / CG_ITERS, 4), "iterations": CG_ITERS, "n_gpus": world, "scaling": "strong",
+           "config": f"BASELINE.json configs[3]: fp64 CG, 5-pt Poisson {CG_GRID}^2 ({n} rows, nnz={nnz}), unpreconditioned "
+                     "(the sample's IC(0)+SpSV preconditioner does not row-shard), x0 = 0, b = 0.75*A*1",
+           "exchange": sh.exchange, "driver": solver.describe(),
+           "residual_first": float(norms[0]), "residual_last": float(norms[-1]), "true_residual_last": float(rr.sqrt().item())}
+    sh.local_op.close()
+    return out
+
+
+def toolkit_cusparse_leg(torch, off, col, val, x, y_ours, steps, warmup, peak):
+    """The closed library as the reference samples link it (CUDA 12.9 toolkit's libcusparse), timed from C: inside this
+    Python process only the copy torch ships can be loaded (cudalibrarysamples_b200/lib.py)."""
+    import numpy as np
+    exe = os.path.join(ROOT, "tools", "_bin", "spmv_timer.cusparse")
+    if not os.path.exists(exe):
+        return {"unavailable": "tools/_bin/spmv_timer.cusparse not built"}
+    rows, nnz = int(off.numel()) - 1, int(col.numel())
+    with tempfile.TemporaryDirectory(prefix="b200spmv_") as d:
+        for name, t in (("off", off), ("col", col), ("val", val), ("x", x)):
+            t.cpu().numpy().tofile(os.path.join(d, name + ".bin"))
+        env = {k: v for k, v in os.environ.items() if k not in ("B200SPMV_CUSPARSE", "LD_PRELOAD")}
+        p = subprocess.run([exe, d, str(rows), str(rows), str(nnz), str(steps), str(max(warmup, 3)), "cusparse"],
+                           capture_output=True, text=True, timeout=180, env=env)
+        if p.returncode != 0:
+            return {"error": (p.stdout + p.stderr)[-400:]}
+        res = json.loads(p.stdout.strip().splitlines()[-1])
+        y = np.fromfile(os.path.join(d, "y_cusparse.bin"), dtype=np.float64)
+    nbytes = csr_bytes(rows, rows, nnz)
+    us = res["us_per_spmv"]
+    yo = y_ours.cpu().numpy()
+    return {"value": round(nbytes / us / 1e3, 3), "unit": UNIT, "us_per_spmv": us, "frac_of_peak": round(nbytes / us / 1e3 / peak, 4),
+            "cusparse_version": res["cusparse_version"], "rel_diff_vs_ours": float(np.linalg.norm(yo - y) / np.linalg.norm(y)),
+            "what": "closed cusparseSpMV of the CUDA 12.9 toolkit (what the reference samples link), preprocessed, timed by "
+                    "tools/spmv_timer.c in its own process on the same matrix (separate process: same box, same loop shape)"}
 
 
 def run_ours(args):
@@ -249,13 +432,11 @@ def run_ours(args):
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; the contract is ONE JSON line on stdout
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
-        # Plain stream order for the fix-up launch next to NCCL kernels: the programmatic early launch buys ~0.5 us on
-        # 100 us, and one 4-GPU run of this script hung for reasons we could not reproduce (profiles/README.md).
-        os.environ.setdefault("B200SPMV_NO_PDL", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     sampler.start()
     api = cs.Api("b200")
+    api.reset_stats()
     peak, peak_src = measured_peak()
 
     rows = ROWS_PER_GPU * world
@@ -263,7 +444,6 @@ def run_ours(args):
     nnz = int(col.numel())
     x = W.uniform(44, rows)
     total_bytes = csr_bytes(rows, rows, nnz)
-    launches_per_step = 2 if nnz >= 12 * rows else 1   # csr_tile_kernel + csr_fixup_kernel, or the single persistent csr_pipe_kernel
 
     if not dist_on:
         op = cs.SpMVOperator(api, "csr", rows, rows, dict(off=off, col=col, val=val), preprocess=True)
@@ -271,28 +451,28 @@ def run_ours(args):
         step = prebuilt_spmv_call(cs, op, x, y)
         kernel_bytes = total_bytes
         local = dict(rows=rows, nnz=nnz)
+        exchange = None
     else:
         def make_local(r, c, arrays):
             lop = cs.SpMVOperator(api, "csr", r, c, arrays, preprocess=True)
             make_local.op = lop
             return lop
-        sh = ShardedCsr(off, col, val, rank, world, make_local, exchange="allgather")   # R-MAT rows read every x block
+        sh = ShardedCsr(off, col, val, rank, world, make_local, exchange=args.exchange)   # R-MAT rows read every x block
         del off, col, val
         torch.cuda.empty_cache()
         xs = sh.new_x_shard(x)
         ys = sh.new_y_shard()
         lop = make_local.op
         local_call = prebuilt_spmv_call(cs, lop, sh.x_full, ys)
-
-        def step():
-            dist.all_gather_into_tensor(sh.x_full, xs)
-            local_call()
+        step = sh.make_step(xs, ys, local_call)
+        exchange = sh.describe_exchange()
         kernel_bytes = csr_bytes(sh.rows, sh.cols_padded, sh.nnz)
         local = dict(rows=sh.rows, nnz=sh.nnz, x_block=sh.x_block)
         # parity of the sharded product at full size: every rank checks its y shard against the closed library run
         # on the same local arrays and the gathered x (max relative difference over ranks goes into the JSON line)
         step()
         torch.cuda.synchronize()
+        dist.barrier()
         capi = cs.Api("cusparse")
         cop = cs.SpMVOperator(capi, "csr", sh.rows, sh.cols_padded, dict(off=sh.off, col=sh.col, val=sh.val), preprocess=True)
         yc = torch.zeros_like(ys)
@@ -310,7 +490,7 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = total_bytes / (ms_step * 1e-3) / 1e9
 
-    # dominant kernel alone (no collective in the loop): average launch duration over the same K launches
+    # dominant kernel alone (no exchange in the loop): average launch duration over the same K launches
     if dist_on:
         for _ in range(3):
             local_call()
@@ -319,6 +499,7 @@ def run_ours(args):
     else:
         kern_ms = ms_step
     achieved = kernel_bytes / (kern_ms * 1e-3) / 1e9
+    stats_hot = api.stats()
 
     # clocks: if the timed region was too short for NVML's sampling period, loop the same step for ~1 s and sample that
     probe = None
@@ -337,20 +518,16 @@ def run_ours(args):
     e2e = None
     if not dist_on:
         hx = x.cpu().pin_memory()
-        hy = torch.empty(rows, dtype=torch.float64).pin_memory()
-        dx, dy = torch.empty_like(x), torch.empty_like(y)
-
-        def e2e_step():
-            dx.copy_(hx, non_blocking=True)
-            op(dx, dy, 1.0, 0.0)
-            hy.copy_(dy, non_blocking=True)
-        for _ in range(3):
-            e2e_step()
-        ms_e, _, _ = time_steps(torch, e2e_step, args.steps, False)
+        pipe = PipelinedE2E(torch, op, hx, rows, rows)
+        for _ in range(4):
+            pipe.step()
+        pipe.drain()
+        ms_e, _, _ = time_steps(torch, pipe.step, args.steps, False, tail=pipe.drain)
         e2e = {"value": round(total_bytes / (ms_e / args.steps * 1e-3) / 1e9, 3), "unit": UNIT,
                "h2d_bytes_per_step": rows * 8, "d2h_bytes_per_step": rows * 8, "ms_per_step": round(ms_e / args.steps, 4),
-               "what": "pinned host x -> device, cusparseSpMV through the C ABI, device y -> pinned host, every step; A resident"}
-        assert torch.equal(hy, y.cpu()), "e2e result differs from the device-resident result"
+               "what": "every step: pinned host x -> device, cusparseSpMV through the C ABI, device y -> pinned host; A resident; "
+                       "the copies of neighbouring steps overlap the kernel (two device buffer sets, two copy streams)"}
+        assert torch.equal(pipe.last_result(), y.cpu()), "e2e result differs from the device-resident result"
     else:
         hx = xs.cpu().pin_memory()
         hy = torch.empty(max(sh.rows, 1), dtype=torch.float64).pin_memory()[:sh.rows]
@@ -365,11 +542,13 @@ def run_ours(args):
         e2e = {"value": round(total_bytes / (ms_e / args.steps * 1e-3) / 1e9, 3), "unit": UNIT,
                "h2d_bytes_per_step": sh.x_block * 8 * world, "d2h_bytes_per_step": rows * 8,
                "ms_per_step": round(ms_e / args.steps, 4),
-               "what": "per rank: pinned host x shard -> device, all-gather + cusparseSpMV, device y shard -> pinned host"}
+               "what": "per rank: pinned host x shard -> device, x exchange + cusparseSpMV, device y shard -> pinned host"}
 
     # ---- closed cusparseSpMV (csrmv_v3_kernel, sm_100 SASS) on the same device buffers: the on-box bar to beat ----
-    closed = None
+    closed = toolkit = None
     if not dist_on and not args.no_cusparse:
+        step = prebuilt_spmv_call(cs, op, x, y)
+        step()
         try:
             capi = cs.Api("cusparse")
             cop = cs.SpMVOperator(capi, "csr", rows, rows, dict(off=off, col=col, val=val), preprocess=True)
@@ -385,22 +564,50 @@ def run_ours(args):
             cop.close()
         except Exception as e:  # pragma: no cover
             closed = {"error": repr(e)}
+        try:
+            toolkit = toolkit_cusparse_leg(torch, off, col, val, x, y, args.steps, args.warmup, peak)
+        except Exception as e:  # pragma: no cover
+            toolkit = {"error": repr(e)}
 
     # ---- cpu_baseline: the oracle port on this box's host cores, rank 0, N=1 only, bounded sample ----
     cpu = None
     if not dist_on and not args.no_cpu:
         h_off, h_col, h_val, h_x = (t.cpu().numpy() for t in (off, col, val, x))
-        gbs, threads, best, times = cpu_reference(h_off, h_col, h_val, h_x, reps=5)
+        threads = host_threads()
+        med, times, ref = cpu_times(h_off, h_col, h_val, h_x, threads, 21)
+        gbs = csr_bytes(rows, rows, nnz) / med / 1e9
         # correctness of the measured result against the oracle, at full size
-        from oracle import oracle as O
-        ref = O.spmv_csr(h_off, h_col, h_val, h_x, threads=threads)
         rel = float(np.linalg.norm(y.cpu().numpy() - ref) / np.linalg.norm(ref))
         assert rel < 1e-12, f"GPU result differs from the CPU oracle: {rel}"
-        cpu = {"value": round(gbs, 3), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"the full {rows}-row matrix, 5 repetitions, min ({best * 1e3:.1f} ms); OpenMP dynamic row chunks",
+        cpu = {"value": round(gbs, 3), "unit": UNIT, "cores": threads, "kind": "port", "statistic": "median",
+               "sample": f"the full {rows}-row matrix, 21 repetitions, median ({med * 1e3:.2f} ms; min {min(times) * 1e3:.2f}); OpenMP dynamic row chunks",
                "gpu_vs_oracle_rel_err": rel}
 
+    # ---- extra legs: north-star size, CG ----
+    north = cg = None
+    if not dist_on:
+        op.close()
+        del off, col, val, x, y
+        torch.cuda.empty_cache()
+        if not args.no_extra:
+            try:
+                north = north_star_leg(torch, cs, W, api, peak, max(20, args.steps // 4))
+            except Exception as e:  # pragma: no cover
+                north = {"error": repr(e)}
+            torch.cuda.empty_cache()
+    else:
+        lop.close()
+        del sh, xs, ys
+        torch.cuda.empty_cache()
+    if not args.no_extra:
+        try:
+            cg = cg_leg(torch, dist, cs, W, api, rank, world)
+        except Exception as e:  # pragma: no cover
+            cg = {"error": repr(e)}
+
     if rank == 0:
+        kname = api.last_csr_kernel()
+        launches = {"b200::csr_seg_kernel<double>": 2, "b200::csr_tile_kernel<double>": 2, "b200::csr_rowwise_kernel<double>": 2}.get(kname, 1)
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -408,16 +615,23 @@ def run_ours(args):
             "gflops": round(2 * nnz / (ms_step * 1e-3) / 1e9, 3),
             "frac_of_hbm_peak": round(value / (peak * world), 4),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "kernel": "b200::csr_tile_kernel<double>", "kernel_avg_us": round(kern_ms * 1e3, 3),
+                         "traffic": None, "kernel": kname, "kernel_avg_us": round(kern_ms * 1e3, 3),
                          "algorithmic_bytes_per_launch": kernel_bytes, "peak_source": peak_src,
                          "per_rank": local},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
-            "cusparse_same_box": closed, "impl": "b200",
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches * args.steps, "clocks": clocks,
+            "cusparse_same_box": closed, "cusparse_toolkit": toolkit, "north_star_10m": north, "cg_config4": cg,
+            "exchange": exchange, "forwarded_calls_in_timed_region": stats_hot["forwarded"], "impl": "b200",
         }
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
-                line["roofline"]["traffic"] = json.load(open(prof)).get("csr_tile_kernel_f64_rmat1m_dram_bytes")
+                t = json.load(open(prof))
+                if t.get("source_sha") == kernel_source_sha() and t.get("kernel") == kname and world == 1:
+                    line["roofline"]["traffic"] = t.get("dram_bytes_per_launch")
+                    line["roofline"]["traffic_source"] = t.get("ncu_report")
+                else:
+                    line["roofline"]["traffic_note"] = ("profiles/traffic.json was captured from other kernel sources / another kernel / "
+                                                        "another shard size: not quoted")
             except Exception:
                 pass
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
@@ -432,7 +646,7 @@ def main():
     global _REAL_STDOUT
     # Watchdog: a distributed hang must not wedge the GPU box -- dump every thread's stack and exit after the limit.
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "900" if "--impl" in sys.argv and "reference" in sys.argv else "240")), exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "900" if "--impl" in sys.argv and "reference" in sys.argv else "420")), exit=True)
     sys.stdout.flush()
     _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
@@ -441,8 +655,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--exchange", default="auto", help="N>1: how x is exchanged (auto | allgather | p2p)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-cusparse", action="store_true", help="skip the closed-library comparison leg")
+    ap.add_argument("--no-cusparse", action="store_true", help="skip the closed-library comparison legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the north-star and CG legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -55,3 +55,22 @@ def conjugate_gradient(sh: ShardedCsr, b_shard: torch.Tensor, iters: int, x0_sha
         torch.addcmul(r, p, beta, out=p)               # P = beta P + R (cg_example.c:280-286), one pass
         delta = delta_new
     return x, torch.cat(norms)
+
+
+class CgSolver:
+    """conjugate_gradient() packaged for repeated timed runs (bench.py's cg_config4 leg, scripts/cg_bench.py)."""
+
+    def __init__(self, sh: ShardedCsr, b_shard: torch.Tensor):
+        self.sh, self.b = sh, b_shard
+
+    def run(self, iters: int):
+        x, norms = conjugate_gradient(self.sh, self.b, iters)
+        return x, [float(v) for v in norms.tolist()]
+
+    def describe(self) -> str:
+        return ("plain CG (cg_example.c:215-287 without the IC(0) preconditioner), SpMV through the C ABI, vector updates as "
+                "single-pass torch ops (addcmul), dots all-reduced over ranks, no host synchronisation inside the loop")
+
+
+def make_cg_solver(sh: ShardedCsr, b_shard: torch.Tensor) -> CgSolver:
+    return CgSolver(sh, b_shard)

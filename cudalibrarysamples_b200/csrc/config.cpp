@@ -32,6 +32,14 @@ static int apply(Config& c, const char* key, const char* value) {
     if (!strcmp(key, "B200SPMV_TILE_ORDER")) { c.tile_scatter = value && !strcmp(value, "scatter"); return 0; }
     if (!strcmp(key, "B200SPMV_PDL")) { c.pdl = truthy(value); return 0; }
     if (!strcmp(key, "B200SPMV_SEG_DENSE")) { c.seg_dense = (value && value[0]) ? atoi(value) : 24; if (c.seg_dense < 1) c.seg_dense = 1; return 0; }
+    if (!strcmp(key, "B200SPMV_FLAT")) {
+        if (!value || !value[0] || !strcmp(value, "auto")) c.flat = -1;
+        else if (!strcmp(value, "on")) c.flat = 1;
+        else if (!strcmp(value, "off")) c.flat = 0;
+        else return -1;
+        return 0;
+    }
+    if (!strcmp(key, "B200SPMV_FLAT_QUIET")) { c.flat_quiet_permille = (value && value[0]) ? atoi(value) : 350; return 0; }
     if (!strcmp(key, "B200SPMV_SELL_GENERIC")) { c.sell_generic = truthy(value); return 0; }
     return -1;
 }
@@ -41,7 +49,7 @@ Config& config() {
     static std::once_flag once;
     std::call_once(once, [] {
         static const char* keys[] = {"B200SPMV_CSR_KERNEL", "B200SPMV_COO_KERNEL", "B200SPMV_TILE_ORDER", "B200SPMV_PDL",
-                                     "B200SPMV_SEG_DENSE", "B200SPMV_SELL_GENERIC"};
+                                     "B200SPMV_SEG_DENSE", "B200SPMV_SELL_GENERIC", "B200SPMV_FLAT", "B200SPMV_FLAT_QUIET"};
         for (const char* k : keys)
             if (const char* v = getenv(k)) apply(c, k, v);
     });
@@ -70,5 +78,7 @@ void b200spmv_get_stats(uint64_t* native_calls, uint64_t* forwarded_calls, uint6
 }
 
 void b200spmv_reset_stats(void) { b200::stats() = b200::Stats(); }
+
+const char* b200spmv_last_csr_kernel(void) { return b200::stats().last_csr_kernel; }
 
 }  // extern "C"

@@ -10,6 +10,8 @@ struct Config {
     int pdl         = 0;    // B200SPMV_PDL = 1: launch the CSR fix-up kernel with programmatic stream serialization
     int seg_dense   = 24;   // B200SPMV_SEG_DENSE: csr_seg_kernel takes the register path for tiles with >= this many nnz per row
     int sell_generic = 0;   // B200SPMV_SELL_GENERIC = 1: never use the slice-32 specialisation
+    int flat        = -1;   // B200SPMV_FLAT = auto|on|off: the preprocess-built flat CSR plan (csr_flat_kernel); auto = by the matrix' row statistic
+    int flat_quiet_permille = 350;   // B200SPMV_FLAT_QUIET: auto picks the flat kernel when at least this share of the 32-non-zero steps ends no row
     int coo_kernel  = -1;   // B200SPMV_COO_KERNEL = tile|seg ; -1 = default (seg)
 };
 
@@ -18,6 +20,7 @@ Config& config();
 // counters a test can read: how many SpMV calls ran on our kernels / were handed to the closed library
 struct Stats {
     unsigned long long native_calls = 0, forwarded_calls = 0, analyze_calls = 0;
+    const char* last_csr_kernel = "none";   // name of the main kernel of the most recent CSR launch
 };
 Stats& stats();
 

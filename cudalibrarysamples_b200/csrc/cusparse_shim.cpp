@@ -109,6 +109,7 @@ struct MatInfo {
     cusparseIndexBase_t  base = CUSPARSE_INDEX_BASE_ZERO;
     cudaDataType         vtype = CUDA_R_32F;
     int64_t              sell_values_size = 0, slice_size = 0;
+    bool                 use_flat = false;       // preprocess built the flat plan and the row statistic favours csr_flat_kernel
     void*                plan_buffer = nullptr;  // externalBuffer holding this matrix' CSR plan: set ONLY by cusparseSpMV_preprocess
 };
 struct VecInfo {
@@ -198,6 +199,17 @@ void logf(const char* what, const MatInfo& m) {
 }
 
 }  // namespace
+
+// Layout of the caller's externalBuffer for CSR: [tile plan | flat plan (only for matrices that can profit: >= 8 nnz/row)].
+static bool flat_eligible(const MatInfo& m) {
+    const int mode = b200::config().flat;          // on: every CSR matrix with non-zeros; auto: only where long rows are possible
+    return m.nnz > 0 && mode != 0 && (mode == 1 || m.nnz >= 8 * m.rows);
+}
+static size_t flat_plan_offset(const MatInfo& m) { return (b200spmv_csr_workspace_bytes(m.rows, m.nnz) + 255) / 256 * 256; }
+static size_t csr_buffer_bytes(const MatInfo& m) {
+    return flat_eligible(m) ? flat_plan_offset(m) + b200spmv_csr_flat_workspace_bytes(m.rows, m.nnz)
+                            : b200spmv_csr_workspace_bytes(m.rows, m.nnz);
+}
 
 extern "C" {
 
@@ -310,6 +322,7 @@ cusparseStatus_t cusparseCsrSetPointers(cusparseSpMatDescr_t d, void* off, void*
         if (it != g_mats.end()) {
             it->second.offsets = off; it->second.col_ind = col; it->second.values = val;
             it->second.plan_buffer = nullptr;  // structure may have changed: re-analyse on the next SpMV
+            it->second.use_flat = false;
         }
     }
     return st;
@@ -392,7 +405,7 @@ cusparseStatus_t cusparseSpMV_bufferSize(cusparseHandle_t handle, cusparseOperat
     }
     if (st != CUSPARSE_STATUS_SUCCESS) return st;  // the real library rejected the arguments: keep its verdict
     size_t ours = 0;
-    if (m.format == CUSPARSE_FORMAT_CSR) ours = b200spmv_csr_workspace_bytes(m.rows, m.nnz);
+    if (m.format == CUSPARSE_FORMAT_CSR) ours = csr_buffer_bytes(m);
     else if (m.format == CUSPARSE_FORMAT_COO) ours = b200spmv_coo_workspace_bytes(m.rows, m.nnz);
     else ours = b200spmv_sell_workspace_bytes(m.rows, m.sell_values_size, m.slice_size);
     *bufferSize = ours > real_size ? ours : real_size;
@@ -441,9 +454,35 @@ cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t handle, cusparseOperat
     logf("preprocess(csr plan)", m);
     st = build_csr_plan(stream, m, externalBuffer);
     if (st != CUSPARSE_STATUS_SUCCESS) return st;
+    // The flat plan, and the decision whether this matrix runs on csr_flat_kernel: the share of 32-non-zero steps in
+    // which no row ends (R-MAT 1M: 69 %, uniform 16 per row or stencils: 0 %).  Reading the statistic back synchronises
+    // the stream once, here in preprocess; while the stream is being captured the read-back is skipped and the tile
+    // kernels stay in charge.
+    bool use_flat = false;
+    if (flat_eligible(m)) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusNone;
+        if (cap == cudaStreamCaptureStatusNone) {
+            char* fws = (char*)externalBuffer + flat_plan_offset(m);
+            int rc = b200spmv_csr_flat_analyze((void*)stream, m.rows, m.nnz, m.offsets, (int32_t)m.base, fws);
+            if (rc != 0) return to_status(rc);
+            size_t o_ctl = 0;
+            b200spmv_csr_flat_plan_offsets(m.rows, m.nnz, nullptr, nullptr, nullptr, &o_ctl);
+            int ctl[4] = {0, 0, 0, 0};
+            if (cudaMemcpyAsync(ctl, fws + o_ctl, sizeof ctl, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                cudaStreamSynchronize(stream) != cudaSuccess)
+                return CUSPARSE_STATUS_EXECUTION_FAILED;
+            const int mode = b200::config().flat;
+            use_flat = mode == 1 || (mode < 0 && ctl[2] > 0 &&
+                                     (long long)ctl[1] * 1000 >= (long long)b200::config().flat_quiet_permille * ctl[2]);
+            if (R.log) fprintf(stderr, "[b200spmv] flat plan: %d non-empty rows, %d of %d steps end no row -> %s\n", ctl[0], ctl[1],
+                               ctl[2], use_flat ? "csr_flat_kernel" : "tile kernels");
+        }
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_mats.find((const void*)matA);
     if (it != g_mats.end()) {
+        it->second.use_flat = use_flat;
         it->second.plan_buffer = externalBuffer;
         g_plan_owner[externalBuffer] = it->second.uid;     // a buffer holds one matrix' plan: the latest preprocess wins
     }
@@ -485,7 +524,15 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
             b200::stats().forwarded_calls++;
             return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
         }
-        if (!plan_is_trusted(m, externalBuffer)) {
+        const bool trusted = plan_is_trusted(m, externalBuffer);
+        if (trusted && m.use_flat) {
+            logf("SpMV csr_flat_kernel", m);
+            rc = b200spmv_csr_flat_mv((void*)stream, dt, m.rows, m.cols, m.nnz, m.col_ind, m.values, (int32_t)m.base, alpha, beta,
+                                      on_dev, x.values, (void*)y.values, (char*)externalBuffer + flat_plan_offset(m));
+            b200::stats().native_calls++;
+            return to_status(rc);
+        }
+        if (!trusted) {
             st = build_csr_plan(stream, m, externalBuffer);
             if (st != CUSPARSE_STATUS_SUCCESS) return st;
         }

@@ -1331,9 +1331,15 @@ static int launch_csr(cudaStream_t stream, int64_t rows, int64_t nnz, const void
     // register accumulation (seg).  B200SPMV_CSR_KERNEL=tile|pipe|ws|rowwise|seg (or b200spmv_set_option) overrides,
     // as does -DB200_CSR_KERNEL at build time.
     int mode = B200_CSR_KERNEL;
-    if (mode < 0) mode = cf.csr_kernel >= 0 ? cf.csr_kernel : (nnz >= 12 * rows ? 5 : 1);
+    if (mode < 0) mode = cf.csr_kernel >= 0 ? cf.csr_kernel : (nnz >= 12 * rows ? 0 : 1);
     if (mode == 2 && (((uintptr_t)col | (uintptr_t)val | (uintptr_t)off) & 15) != 0) mode = 1;   // TMA needs 16 B alignment
     cudaError_t err = cudaSuccess;
+    constexpr bool F64 = sizeof(T) == 8;
+    stats().last_csr_kernel = mode == 0 ? (F64 ? "b200::csr_tile_kernel<double>" : "b200::csr_tile_kernel<float>")
+                            : mode == 5 ? (F64 ? "b200::csr_seg_kernel<double>" : "b200::csr_seg_kernel<float>")
+                            : mode == 3 ? (F64 ? "b200::csr_rowwise_kernel<double>" : "b200::csr_rowwise_kernel<float>")
+                            : mode == 2 ? (F64 ? "b200::csr_ws_kernel<double>" : "b200::csr_ws_kernel<float>")
+                                        : (F64 ? "b200::csr_pipe_kernel<double>" : "b200::csr_pipe_kernel<float>");
     if (mode == 0 || mode == 3 || mode == 5) {
         if (mode == 0)      csr_tile_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);
         else if (mode == 5) csr_seg_kernel<T><<<(unsigned)nt, CSR_BLOCK, 0, stream>>>(a);

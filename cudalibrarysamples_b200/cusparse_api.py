@@ -90,6 +90,11 @@ class Api:
         (self.lib if self.impl == "b200" else _lib.shim()).b200spmv_get_stats(C.byref(n), C.byref(f), C.byref(a))
         return dict(native=int(n.value), forwarded=int(f.value), analyze=int(a.value))
 
+    def last_csr_kernel(self) -> str:
+        lib = self.lib if self.impl == "b200" else _lib.shim()
+        lib.b200spmv_last_csr_kernel.restype = C.c_char_p
+        return lib.b200spmv_last_csr_kernel().decode()
+
     def reset_stats(self) -> None:
         (self.lib if self.impl == "b200" else _lib.shim()).b200spmv_reset_stats()
 

@@ -58,6 +58,23 @@ B200SPMV_EXPORT size_t  b200spmv_csr_plan_tiles_offset(void);
 B200SPMV_EXPORT size_t  b200spmv_csr_plan_ctl_offset(int64_t rows, int64_t nnz);
 B200SPMV_EXPORT size_t  b200spmv_csr_plan_split_offset(int64_t rows, int64_t nnz);
 
+/* CSR, "flat" plan (spmv_csr_flat.cu): a second, larger structure-only plan -- one bit per non-zero marking row ends, a
+ * run counter per 256 non-zeros, the list of non-empty rows -- built once by cusparseSpMV_preprocess for matrices with
+ * long / skewed rows; the SpMV kernel then needs no row offsets, no shared-memory staging and no barriers inside a warp's
+ * chunk.  Same call sites as above (spmv_csr_example.c:104-112: preprocess, then SpMV). */
+B200SPMV_EXPORT size_t b200spmv_csr_flat_workspace_bytes(int64_t rows, int64_t nnz);
+B200SPMV_EXPORT int    b200spmv_csr_flat_analyze(void* stream, int64_t rows, int64_t nnz, const void* row_offsets,
+                                                 int32_t base, void* workspace);
+B200SPMV_EXPORT int    b200spmv_csr_flat_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz,
+                                            const void* col_ind, const void* values, int32_t base, const void* alpha,
+                                            const void* beta, int scalars_on_device, const void* x, void* y,
+                                            void* workspace);
+/* byte offsets of the flat plan's arrays inside its workspace: endmask (uint32 per 32 non-zeros, zero-padded to a
+ * multiple of 64 words), chunk_run (int32 per 256 non-zeros + 1), nzrow (int32, rows + 2), control words
+ * {non-empty rows, steps without a row end, steps} -- read back by the bit-exact preprocessing tests */
+B200SPMV_EXPORT void   b200spmv_csr_flat_plan_offsets(int64_t rows, int64_t nnz, size_t* endmask, size_t* chunk_run,
+                                                      size_t* nzrow, size_t* ctl);
+
 /* COO (row-sorted or not).  Replaces cusparseSpMV for cusparseCreateCoo descriptors
  * (cuSPARSE/spmv_coo/spmv_coo_example.c:86-104). */
 B200SPMV_EXPORT size_t b200spmv_coo_workspace_bytes(int64_t rows, int64_t nnz);
@@ -77,6 +94,7 @@ B200SPMV_EXPORT int    b200spmv_sell_mv(void* stream, int dtype, int64_t rows, i
 /* Run-time switches (tests / tuning sweeps; never needed by a caller).  The environment variables of the same names
  * are read ONCE at first use; afterwards only this call changes them.  Not thread-safe against concurrent launches.
  *   B200SPMV_CSR_KERNEL = auto|tile|pipe|ws|rowwise|seg     B200SPMV_COO_KERNEL = auto|tile|seg
+ *   B200SPMV_FLAT = auto|on|off   B200SPMV_FLAT_QUIET = <permille>
  *   B200SPMV_TILE_ORDER = scatter|linear   B200SPMV_PDL = 0|1   B200SPMV_SEG_DENSE = <nnz per row>   B200SPMV_SELL_GENERIC = 0|1
  * returns 0, or -1 for an unknown key / value. */
 B200SPMV_EXPORT int  b200spmv_set_option(const char* key, const char* value);
@@ -85,6 +103,8 @@ B200SPMV_EXPORT int  b200spmv_set_option(const char* key, const char* value);
  * forwarded == 0 on the hot path. */
 B200SPMV_EXPORT void b200spmv_get_stats(uint64_t* native_calls, uint64_t* forwarded_calls, uint64_t* analyze_calls);
 B200SPMV_EXPORT void b200spmv_reset_stats(void);
+/* name of the main kernel the most recent CSR SpMV launched, e.g. "b200::csr_seg_kernel<double>" (bench.py's roofline.kernel) */
+B200SPMV_EXPORT const char* b200spmv_last_csr_kernel(void);
 
 B200SPMV_EXPORT const char* b200spmv_version(void);
 

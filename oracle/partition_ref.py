@@ -82,3 +82,33 @@ def split_rows(tiles, off, base, tile_items):
         if b == b1 + 1:
             out.append((rr, b1, b2))
     return sorted(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# flat plan (b200spmv_csr_flat_analyze in cudalibrarysamples_b200/csrc/spmv_csr_flat.cu): integer preprocessing, bit-exact
+# ---------------------------------------------------------------------------------------------------------------------
+FLAT_CHUNK = 256          # non-zeros per warp chunk
+FLAT_CTA_NNZ = 2048       # non-zeros per CTA
+
+
+def flat_plan(off, base):
+    """numpy restatement of the flat CSR plan:
+       endmask[w] bit i  <=> non-zero 32*w+i is the last one of its row (zero-padded to whole CTAs of 2048 non-zeros),
+       chunk_run[c]      =   number of rows that end before non-zero 256*c   (c = 0 .. nchunks),
+       nzrow             =   [-1] + [indices of the non-empty rows] + [rows],
+       ctl               =   (non-empty rows, 32-non-zero steps in which no row ends, steps)."""
+    off = np.asarray(off, np.int64) - base
+    rows = off.size - 1
+    nnz = int(off[-1])
+    nz = np.diff(off) > 0
+    ends = off[1:][nz] - 1
+    nctas = (nnz + FLAT_CTA_NNZ - 1) // FLAT_CTA_NNZ
+    mask = np.zeros(nctas * (FLAT_CTA_NNZ // 32), np.uint32)
+    np.bitwise_or.at(mask, ends >> 5, (np.uint32(1) << (ends & 31).astype(np.uint32)))
+    nchunks = nctas * (FLAT_CTA_NNZ // FLAT_CHUNK)
+    per_chunk = np.bincount(ends // FLAT_CHUNK, minlength=nchunks)[:nchunks] if nchunks else np.zeros(0, np.int64)
+    chunk_run = np.concatenate([[0], np.cumsum(per_chunk)]).astype(np.int32)
+    nzrow = np.concatenate([[-1], np.nonzero(nz)[0], [rows]]).astype(np.int32)
+    steps = (nnz + 31) // 32
+    quiet = int(np.count_nonzero(mask[:steps] == 0))
+    return mask, chunk_run, nzrow, (int(nz.sum()), quiet, steps)

@@ -94,11 +94,15 @@ if os.environ.get("SWEEP_SET") == "seg":
     VARIANTS["seg_t1024_b128_occ12_k4_st1"] = dict(SEG=(12, 4, 1), TILE=1024, LONG=256, BLOCK=128)
     VARIANTS["seg_t512_b128_occ12_k2_st0"] = dict(SEG=(12, 2, 0), TILE=512, LONG=128, BLOCK=128)
     VARIANTS["seg_t3072_b384_occ4_k4_st0"] = dict(SEG=(4, 4, 0), TILE=3072, LONG=512, BLOCK=384)
+if os.environ.get("SWEEP_SET") == "flat":
+    VARIANTS = {f"flat_occ{o}_k{k}": dict(FLAT=(o, k)) for (o, k) in [(3, 4), (4, 4), (5, 4), (6, 4), (4, 2), (5, 2), (6, 2), (8, 2), (3, 8), (4, 8)]}
 if os.environ.get("SWEEP_SET") == "ablate":
     VARIANTS = dict(ABL, t2048_b256_k4_occ6=VARIANTS["t2048_b256_k4_occ6"])
 
 
 def flags(v):
+    if "FLAT" in v:
+        return [f"-DB200_FLAT_MIN_CTAS={v['FLAT'][0]}", f"-DB200_FLAT_BATCH={v['FLAT'][1]}"]
     if "SEG" in v:
         o, k, staged = v["SEG"]
         base = dict(TILE=v.get("TILE", 2048), LONG=v.get("LONG", 512), BLOCK=v.get("BLOCK", 256), BATCH=4, MIN=5)
@@ -128,7 +132,7 @@ def build():
         out = os.path.join(VDIR, f"libb200spmv_{tag}.so")
         b.build_native(extra_flags=flags(v), out_path=out, tag="v_" + tag)
         log = open(os.path.join(ROOT, "cudalibrarysamples_b200", "build", "v_" + tag, "build.log")).read()
-        i = log.find("csr_seg_kernelIdEE") if "SEG" in v else log.find("csr_rowwise_kernelIdEE") if "RW" in v else log.find("csr_ws_kernelIdEE") if "WS" in v else max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
+        i = log.find("csr_flat_kernelIdEE") if "FLAT" in v else log.find("csr_seg_kernelIdEE") if "SEG" in v else log.find("csr_rowwise_kernelIdEE") if "RW" in v else log.find("csr_ws_kernelIdEE") if "WS" in v else max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
         regs = log[i:i + 400].split("Used ")[1].split(",")[0] if i >= 0 else "?"
         print(tag, regs)
 
@@ -166,7 +170,7 @@ def run(workloads, variants=None, steps=100):
     libs = [("default", None)] + [(t, os.path.join(VDIR, f"libb200spmv_{t}.so")) for t in VARIANTS if (variants is None or t in variants)]
     libs = [(t, p) for t, p in libs if p is None or os.path.exists(p)]
     if os.environ.get("SWEEP_SET") == "kernels":     # every CSR kernel of the default library, picked through b200spmv_set_option
-        libs = [("default", None)] + [("kernel:" + k, None) for k in ("tile", "pipe", "seg", "seg:1", "seg:8", "seg:16", "seg:48", "rowwise", "ws")]
+        libs = [("default", None)] + [("kernel:" + k, None) for k in ("flat", "tile", "pipe", "seg", "seg:48", "rowwise")]
     for wl in workloads:
         rows, off, col, val = make_workload(wl)
         nnz = int(col.numel())
@@ -178,7 +182,8 @@ def run(workloads, variants=None, steps=100):
             api = cs.Api("cusparse") if tag == "cusparse" else cs.Api("b200", lib_path=path)
             if tag != "cusparse":
                 parts = tag.split(":") if tag.startswith("kernel:") else ["", "auto"]
-                api.set_option("B200SPMV_CSR_KERNEL", parts[1])
+                api.set_option("B200SPMV_FLAT", "on" if parts[1] == "flat" else "auto" if parts[1] == "auto" else "off")
+                api.set_option("B200SPMV_CSR_KERNEL", "auto" if parts[1] == "flat" else parts[1])
                 api.set_option("B200SPMV_SEG_DENSE", parts[2] if len(parts) > 2 else "24")
             op = cs.SpMVOperator(api, "csr", rows, rows, dict(off=off, col=col, val=val))
             y = torch.zeros(rows, dtype=torch.float64, device="cuda")

@@ -244,17 +244,21 @@ def test_csr_base_one(cs, b200, closed, dtype):
     assert relerr(got.cpu().numpy(), lib.cpu().numpy()) < TOL[dtype]
 
 
-@pytest.fixture(params=["tile", "pipe", "ws", "rowwise", "seg", "seg:1", "seg:1000000"])
+@pytest.fixture(params=["tile", "pipe", "ws", "rowwise", "seg", "seg:1", "seg:1000000", "flat"])
 def csr_kernel(request, b200):
     """Every CSR kernel variant of the library must give the same answers (b200spmv_set_option picks one).
     "seg:N" = csr_seg_kernel with the row-sparse threshold N: 1 sends every tile that has non-zeros down the register
-    path (multi-row steps, > 32 row ends per step), 1000000 sends every tile down the staged-product path."""
+    path (multi-row steps, > 32 row ends per step), 1000000 sends every tile down the staged-product path.
+    "flat" = csr_flat_kernel on the preprocess-built flat plan, forced for every matrix with non-zeros (calls without
+    cusparseSpMV_preprocess still take the tile kernels: the flat plan is only ever built by preprocess)."""
     name, _, dense = request.param.partition(":")
-    b200.set_option("B200SPMV_CSR_KERNEL", name)
+    b200.set_option("B200SPMV_FLAT", "on" if name == "flat" else "off")
+    b200.set_option("B200SPMV_CSR_KERNEL", "auto" if name == "flat" else name)
     b200.set_option("B200SPMV_SEG_DENSE", dense or "24")
     yield request.param
     b200.set_option("B200SPMV_CSR_KERNEL", "auto")
     b200.set_option("B200SPMV_SEG_DENSE", "24")
+    b200.set_option("B200SPMV_FLAT", "auto")
 
 
 @pytest.fixture(params=["tile", "seg"])
@@ -537,6 +541,57 @@ def test_partition_is_bit_exact(cs, b200, case, base):
     assert ctl[0] == 0
     lst = ws[osp:osp + 16 * nsplit].view(torch.int32).view(-1, 4).cpu().numpy()
     assert sorted((int(a), int(b), int(c)) for a, b, c, _ in lst) == split_rows(want, off, base, t.value)
+
+
+@pytest.mark.parametrize("case", ["rmat", "stencil", "huge_then_tiny", "many_rows_end_in_one_step", "leading_empty"])
+@pytest.mark.parametrize("base", [0, 1])
+def test_flat_plan_is_bit_exact(case, base):
+    """The flat CSR plan of cusparseSpMV_preprocess (end-lane bitmask, run counters, non-empty-row table) against its numpy
+    restatement oracle/partition_ref.py::flat_plan -- integer work, bit for bit."""
+    from cudalibrarysamples_b200 import lib
+    from oracle.partition_ref import flat_plan
+    L = lib.shim()
+    L.b200spmv_csr_flat_workspace_bytes.restype = C.c_size_t
+    if case == "rmat":
+        off = O.rmat_csr(200000, avg_nnz=16, seed=5, val_seed=6)[0]
+    elif case == "stencil":
+        off = O.gen_stencil5(300)[0]
+    else:
+        off = np.concatenate([[0], np.cumsum(EDGE[case])]).astype(np.int32)
+    off = off + base
+    rows, nnz = off.size - 1, int(off[-1]) - base
+    ws = torch.full((L.b200spmv_csr_flat_workspace_bytes(C.c_int64(rows), C.c_int64(nnz)),), 0xA5, dtype=torch.uint8, device="cuda")
+    d_off = dev(off)
+    rc = L.b200spmv_csr_flat_analyze(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_int64(rows), C.c_int64(nnz),
+                                     C.c_void_p(d_off.data_ptr()), C.c_int32(base), C.c_void_p(ws.data_ptr()))
+    assert rc == 0
+    torch.cuda.synchronize()
+    om, oc, on, ol = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    L.b200spmv_csr_flat_plan_offsets(C.c_int64(rows), C.c_int64(nnz), C.byref(om), C.byref(oc), C.byref(on), C.byref(ol))
+    mask, chunk_run, nzrow, (nruns, quiet, steps) = flat_plan(off, base)
+    got_mask = ws[om.value:om.value + 4 * mask.size].view(torch.int32).cpu().numpy().view(np.uint32)
+    got_run = ws[oc.value:oc.value + 4 * chunk_run.size].view(torch.int32).cpu().numpy()
+    got_nzrow = ws[on.value:on.value + 4 * nzrow.size].view(torch.int32).cpu().numpy()
+    ctl = ws[ol.value:ol.value + 16].view(torch.int32).cpu().numpy()
+    assert np.array_equal(got_mask, mask)
+    assert np.array_equal(got_run, chunk_run)
+    assert np.array_equal(got_nzrow, nzrow)
+    assert (int(ctl[0]), int(ctl[1]), int(ctl[2])) == (nruns, quiet, steps) and int(ctl[3]) == nruns
+
+
+def test_flat_kernel_is_chosen_for_skewed_rows_only(cs, b200):
+    """auto: preprocess reads the row statistic back and picks csr_flat_kernel for R-MAT, the tile kernels for a stencil."""
+    off, col, val, x, y0 = rmat_case(60000, 16, torch.float64, 21)
+    run(cs, b200, "csr", 60000, 60000, dict(off=dev(off), col=dev(col), val=dev(val)), dev(x), dev(y0), 1.0, 0.0)
+    assert "csr_flat_kernel" in b200.last_csr_kernel()
+    run(cs, b200, "csr", 60000, 60000, dict(off=dev(off), col=dev(col), val=dev(val)), dev(x), dev(y0), 1.0, 0.0, preprocess=False)
+    assert "csr_flat_kernel" not in b200.last_csr_kernel()
+    rows = 40000
+    col16 = np.sort(np.random.default_rng(0).integers(0, rows, (rows, 16)), axis=1).astype(np.int32).reshape(-1)
+    off16 = (np.arange(rows + 1) * 16).astype(np.int32)
+    val16 = O.uniform(3, rows * 16)
+    run(cs, b200, "csr", rows, rows, dict(off=dev(off16), col=dev(col16), val=dev(val16)), dev(O.uniform(4, rows)), dev(O.uniform(5, rows)), 1.0, 0.0)
+    assert "csr_flat_kernel" not in b200.last_csr_kernel()
 
 
 def test_device_generators_are_bit_identical_to_the_oracle():
