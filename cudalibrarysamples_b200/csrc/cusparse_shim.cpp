@@ -54,6 +54,11 @@ struct Real {
     REAL_FN(cusparseConstCsrGet)
     REAL_FN(cusparseConstCooGet)
     REAL_FN(cusparseConstDnVecGet)
+    REAL_FN(cusparseSpMM_bufferSize)
+    REAL_FN(cusparseSpMM_preprocess)
+    REAL_FN(cusparseSpMM)
+    REAL_FN(cusparseConstDnMatGet)
+    REAL_FN(cusparseDnMatGetStridedBatch)
 #undef REAL_FN
     bool forward = false, log = false;
 };
@@ -87,7 +92,8 @@ void init_real() {
     LOAD(cusparseCreateConstDnVec) LOAD(cusparseDestroyDnVec) LOAD(cusparseDnVecSetValues)
     LOAD(cusparseSpMV_bufferSize) LOAD(cusparseSpMV_preprocess) LOAD(cusparseSpMV) LOAD(cusparseGetStream)
     LOAD(cusparseGetPointerMode) LOAD(cusparseSpMatGetFormat) LOAD(cusparseConstCsrGet) LOAD(cusparseConstCooGet)
-    LOAD(cusparseConstDnVecGet)
+    LOAD(cusparseConstDnVecGet) LOAD(cusparseSpMM_bufferSize) LOAD(cusparseSpMM_preprocess) LOAD(cusparseSpMM)
+    LOAD(cusparseConstDnMatGet) LOAD(cusparseDnMatGetStridedBatch)
 #undef LOAD
     g_real = r;
 }
@@ -548,6 +554,79 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
         rc = b200spmv_sell_mv((void*)stream, dt, m.rows, m.cols, m.slice_size, m.offsets, m.col_ind, m.values,
                               (int32_t)m.base, alpha, beta, on_dev, x.values, (void*)y.values, externalBuffer);
     }
+    b200::stats().native_calls++;
+    return to_status(rc);
+}
+
+// ---------------------------------------------------------------- SpMM (CSR x dense) ---------------------------------
+// Dense-matrix descriptors are the real library's; what our kernel needs is read through cusparseConstDnMatGet.
+struct DnMatInfo {
+    int64_t rows = 0, cols = 0, ld = 0;
+    const void* values = nullptr;
+    cudaDataType vtype = CUDA_R_32F;
+    cusparseOrder_t order = CUSPARSE_ORDER_COL;
+    int batch = 1;
+};
+static bool get_dnmat(cusparseConstDnMatDescr_t d, DnMatInfo* m) {
+    Real& R = real();
+    if (R.cusparseConstDnMatGet(d, &m->rows, &m->cols, &m->ld, &m->values, &m->vtype, &m->order) != CUSPARSE_STATUS_SUCCESS) return false;
+    int64_t stride = 0;
+    if (R.cusparseDnMatGetStridedBatch(d, &m->batch, &stride) != CUSPARSE_STATUS_SUCCESS) m->batch = 1;
+    return true;
+}
+static bool spmm_supported(cusparseOperation_t opA, cusparseOperation_t opB, const MatInfo& a, const DnMatInfo& b, const DnMatInfo& c,
+                           cudaDataType compute) {
+    if (opA != CUSPARSE_OPERATION_NON_TRANSPOSE || opB != CUSPARSE_OPERATION_NON_TRANSPOSE) return false;
+    if (a.format != CUSPARSE_FORMAT_CSR || a.off_type != CUSPARSE_INDEX_32I || a.col_type != CUSPARSE_INDEX_32I) return false;
+    if (dtype_of(a.vtype) < 0 || b.vtype != a.vtype || c.vtype != a.vtype || compute != a.vtype) return false;
+    if (b.batch > 1 || c.batch > 1) return false;                    // strided batches (spmm_csr_batched) stay with the real library
+    if (a.rows >= INT32_MAX || a.cols >= INT32_MAX || a.nnz >= INT32_MAX - 65536 || c.cols >= 64 * 65535) return false;
+    return true;
+}
+
+cusparseStatus_t cusparseSpMM_bufferSize(cusparseHandle_t handle, cusparseOperation_t opA, cusparseOperation_t opB,
+                                         const void* alpha, cusparseConstSpMatDescr_t matA, cusparseConstDnMatDescr_t matB,
+                                         const void* beta, cusparseDnMatDescr_t matC, cudaDataType computeType,
+                                         cusparseSpMMAlg_t alg, size_t* bufferSize) {
+    // our kernel needs no workspace; the real library's answer keeps a forwarded call safe
+    return real().cusparseSpMM_bufferSize(handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg, bufferSize);
+}
+
+cusparseStatus_t cusparseSpMM_preprocess(cusparseHandle_t handle, cusparseOperation_t opA, cusparseOperation_t opB,
+                                         const void* alpha, cusparseConstSpMatDescr_t matA, cusparseConstDnMatDescr_t matB,
+                                         const void* beta, cusparseDnMatDescr_t matC, cudaDataType computeType,
+                                         cusparseSpMMAlg_t alg, void* externalBuffer) {
+    Real& R = real();
+    MatInfo a; DnMatInfo b, c;
+    if (!R.forward && handle && matA && matB && matC && find_mat(matA, &a) && get_dnmat(matB, &b) && get_dnmat(matC, &c) &&
+        spmm_supported(opA, opB, a, b, c, computeType))
+        return CUSPARSE_STATUS_SUCCESS;                              // nothing to analyse
+    return R.cusparseSpMM_preprocess(handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg, externalBuffer);
+}
+
+cusparseStatus_t cusparseSpMM(cusparseHandle_t handle, cusparseOperation_t opA, cusparseOperation_t opB, const void* alpha,
+                              cusparseConstSpMatDescr_t matA, cusparseConstDnMatDescr_t matB, const void* beta,
+                              cusparseDnMatDescr_t matC, cudaDataType computeType, cusparseSpMMAlg_t alg, void* externalBuffer) {
+    Real& R = real();
+    MatInfo a; DnMatInfo b, c;
+    if (R.forward || !handle || !matA || !matB || !matC || !alpha || !beta || !find_mat(matA, &a) || !get_dnmat(matB, &b) ||
+        !get_dnmat(matC, &c) || !spmm_supported(opA, opB, a, b, c, computeType)) {
+        if (R.log) fprintf(stderr, "[b200spmv] SpMM forwarded to libcusparse\n");
+        b200::stats().forwarded_calls++;
+        return R.cusparseSpMM(handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg, externalBuffer);
+    }
+    if (b.rows != a.cols || c.rows != a.rows || b.cols != c.cols) return CUSPARSE_STATUS_INVALID_VALUE;
+    cudaStream_t stream = nullptr;
+    cusparseStatus_t st = R.cusparseGetStream(handle, &stream);
+    if (st != CUSPARSE_STATUS_SUCCESS) return st;
+    cusparsePointerMode_t pm = CUSPARSE_POINTER_MODE_HOST;
+    st = R.cusparseGetPointerMode(handle, &pm);
+    if (st != CUSPARSE_STATUS_SUCCESS) return st;
+    if (R.log) fprintf(stderr, "[b200spmv] SpMM spmm_csr_kernel rows=%lld cols=%lld n=%lld nnz=%lld\n", (long long)a.rows,
+                       (long long)a.cols, (long long)c.cols, (long long)a.nnz);
+    const int rc = b200spmm_csr((void*)stream, dtype_of(a.vtype), a.rows, a.cols, c.cols, a.nnz, a.offsets, a.col_ind, a.values,
+                                (int32_t)a.base, alpha, beta, pm == CUSPARSE_POINTER_MODE_DEVICE, b.values, b.ld,
+                                b.order == CUSPARSE_ORDER_ROW, (void*)c.values, c.ld, c.order == CUSPARSE_ORDER_ROW);
     b200::stats().native_calls++;
     return to_status(rc);
 }

@@ -234,6 +234,9 @@ template <typename T>
 __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kernel(const FlatArgs<T> a) {
     __shared__ T   sFirst[FLAT_WARPS], sLast[FLAT_WARPS];
     __shared__ int sFrow[FLAT_WARPS];                      // >= 0: row of the chunk's first row end (deferred to the stitch)
+    __shared__ int sArrived;                               // warps that have deposited their partials
+    if (threadIdx.x == 0) sArrived = 0;
+    __syncthreads();                                       // the only CTA-wide barrier, before any work: nobody waits at the end
 
     const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
     const long long c = (long long)blockIdx.x * FLAT_WARPS + warp;      // warp chunk
@@ -263,36 +266,41 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
             }
         };
         issue(0);
-#pragma unroll
+        // Run-time loops over the steps: with everything unrolled the kernel was 106 KB of SASS and stalled on instruction
+        // fetch (ncu: "no instruction" the top stall reason, 160 us); only the short load / gather loops stay unrolled.
+#pragma unroll 1
         for (int kb = 0; kb < FLAT_STEPS; kb += FLAT_BATCH) {
             if (n0 + kb * 32 >= n1) break;                 // warp-uniform: the matrix' last chunk may be short
             T p[FLAT_BATCH];
 #pragma unroll
             for (int k = 0; k < FLAT_BATCH; k++) p[k] = (n0 + (kb + k) * 32 + lane < n1) ? vv[k] * __ldg(xp + cc[k]) : T(0);
             if (kb + FLAT_BATCH < FLAT_STEPS && n0 + (kb + FLAT_BATCH) * 32 < n1) issue(kb + FLAT_BATCH);
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < FLAT_BATCH; k++) {
                 const unsigned m = __shfl_sync(0xffffffffu, mreg, kb + k);
-                const T pk = p[k];
+                T pk = p[0];                               // p[k] with a run-time k: a select chain, not local memory
+#pragma unroll
+                for (int jj = 1; jj < FLAT_BATCH; jj++) pk = k == jj ? p[jj] : pk;
                 if (m == 0u) { acc += pk; continue; }      // the whole step lies inside one row
                 const int e1 = __ffs(m) - 1, ek = 31 - __clz(m);
+                // my row (if I end one): issued first, the look-up's latency hides behind the shuffles below
+                const bool is_end = (m >> lane) & 1u;
+                const int  j = run + __popc(m & ((1u << lane) - 1u));        // index of the row (among non-empty rows) I end
+                int rlo = 0, row = 0;
+                if (is_end) { rlo = __ldg(a.plan.nzrow + j); row = __ldg(a.plan.nzrow + j + 1); }
                 const T t1 = flat_allsum(acc + (lane <= e1 ? pk : T(0)));
                 T q = (lane > e1 && lane <= ek) ? pk : T(0);
                 if (m & (m - 1u)) {                        // more rows end: segmented inclusive scan
                     const unsigned below = m & ((1u << lane) - 1u);
                     const int dist = (lane > e1 && lane <= ek) ? lane - (32 - __clz(below)) : 0;
-#pragma unroll
+#pragma unroll 1
                     for (int d = 1; d < 32; d <<= 1) {
                         if (__ballot_sync(0xffffffffu, dist >= d) == 0u) break;
                         const T t = __shfl_up_sync(0xffffffffu, q, d);
                         if (dist >= d) q += t;
                     }
                 }
-                const T    res = lane == e1 ? t1 : q;
-                const bool is_end = (m >> lane) & 1u;
-                const int  j = run + __popc(m & ((1u << lane) - 1u));        // index of the row (among non-empty rows) I end
-                int rlo = 0, row = 0;
-                if (is_end) { rlo = __ldg(a.plan.nzrow + j); row = __ldg(a.plan.nzrow + j + 1); }
+                const T res = lane == e1 ? t1 : q;
                 if (frow < 0) {                            // the chunk's first row end goes to the stitch
                     first = __shfl_sync(0xffffffffu, res, e1);
                     frow = __shfl_sync(0xffffffffu, row, e1);
@@ -326,14 +334,17 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
         const unsigned ml = __shfl_sync(0xffffffffu, mreg, el >> 5);
         if (!((ml >> (el & 31)) & 1u)) last = flat_allsum(acc);
     }
+    // The warp that deposits its partials LAST stitches the CTA (fixed warp order -> bit-reproducible); the others are gone.
+    int arrived = 0;
     if (lane == 0) {
         if (frow >= 0) { sFirst[warp] = first; sLast[warp] = last; }
         else           { sFirst[warp] = last;  sLast[warp] = T(0); }     // no row ended here: the whole chunk is one partial
         sFrow[warp] = frow;
+        __threadfence_block();
+        arrived = atomicAdd(&sArrived, 1);
     }
-    __syncthreads();
-
-    if (threadIdx.x == 0) {
+    if (lane == 0 && arrived == FLAT_WARPS - 1) {
+        __threadfence_block();
         const long long cta = blockIdx.x;
         const bool starts_row = cta == 0 || (__ldg(a.plan.endmask + cta * FLAT_CTA_WORDS - 1) >> 31);   // a row starts with this CTA
         T    running = T(0);

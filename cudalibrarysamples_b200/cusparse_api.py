@@ -240,6 +240,29 @@ class SpMVOperator:
                        self.alg, self.buffer)
         return y
 
+    def prebuilt(self, x: torch.Tensor, y: torch.Tensor, alpha=1.0, beta=0.0):
+        """A zero-argument callable that issues exactly this cusparseSpMV (fixed x, y, alpha, beta) with the ctypes
+        arguments built once: ~2 us of host time per call instead of ~15 (timing loops, CUDA-graph capture)."""
+        a = self.api
+        a.cusparseDnVecSetValues(self.vecX, x)
+        a.cusparseDnVecSetValues(self.vecY, y)
+        ct = _CT[self.dtype]
+        ca, cb = ct(alpha), ct(beta)
+        fn = a.lib.cusparseSpMV
+        argv = (self.handle, C.c_int(CUSPARSE_OPERATION_NON_TRANSPOSE), C.cast(C.pointer(ca), C.c_void_p), self.mat, self.vecX,
+                C.cast(C.pointer(cb), C.c_void_p), self.vecY, C.c_int(self.ctype), C.c_int(self.alg),
+                C.c_void_p(self.buffer.data_ptr()))
+        vx, vy, setv = self.vecX, self.vecY, a.lib.cusparseDnVecSetValues
+        px, py = C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr())
+
+        def call(_keep=(ca, cb, x, y)):
+            setv(vx, px)            # several prebuilt calls may share this operator's vector descriptors
+            setv(vy, py)
+            st = fn(*argv)
+            if st != 0:
+                raise CuSparseError("cusparseSpMV", st)
+        return call
+
     def close(self):
         if self.mat is not None:
             self.api.cusparseDestroySpMat(self.mat)

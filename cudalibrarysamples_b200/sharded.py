@@ -1,19 +1,33 @@
 """Row-block sharding of a square CSR matrix over the GPUs of one box (one process per GPU, torch.distributed).
 
 SpMV shards naturally by contiguous row blocks: rank g owns rows [R_g, R_{g+1}) of A -- chosen so every
-rank holds ~nnz/G non-zeros, not rows/G, because R-MAT rows are skewed -- plus the matching slice of x and y.  The only
-exchange step of the path is one all-gather of x (NCCL over NVLink 5 / NVSwitch) right before the local kernel; in CG the x
-shard of one product is the y shard of the previous one, so the gather sits on the critical path of every iteration.
+rank holds ~nnz/G non-zeros, not rows/G, because R-MAT rows are skewed -- plus the matching slice of y.  x is distributed in
+EQUAL blocks (not by the row blocks), so the exchange moves exactly |x|*(G-1)/G bytes per rank, no padding, and the
+assembled buffer is x: the local product is an ordinary rows_g x cols CSR SpMV through the same C ABI as the single-GPU
+path, on the caller's unmodified column indices.
 
-x itself is distributed in EQUAL blocks (not by the row blocks), so the gather moves exactly |x|*(G-1)/G bytes per
-rank, no padding, and the gathered buffer is x: the local product is an ordinary rows_g x cols CSR SpMV through the
-same C ABI as the single-GPU path, on the caller's unmodified column indices.
+The exchange of x is the path's only communication step, and in round 1 it was fully exposed (8 GPUs: 177 us of NCCL
+all-gather in front of a 102 us kernel).  Now the local matrix is split ONCE at set-up into two column panels:
+
+    own panel     columns of this rank's own x block  -> needs nothing from the other ranks
+    remote panel  all other columns                   -> needs the assembled x
+
+and a step is:  start the exchange  ||  y = alpha*A_own*x_own + beta*y   ->   wait   ->   y += alpha*A_remote*x.
+Exchange mechanisms (chosen at set-up, structure-only, like the kernels' plans):
+
+    "p2p"        x shards live in symmetric memory (torch.distributed._symmetric_memory: CUDA IPC / fabric handles mapped
+                 into every rank); one device-side barrier, then every rank PULLS the other shards with copy-engine
+                 peer copies over NVLink (no SMs, no NCCL kernels) on side streams, starting with a different peer on every
+                 rank so no source is read by two ranks at once.  Double-buffered shards: one barrier per step suffices.
+    "allgather"  one NCCL all_gather_into_tensor on a side stream (fallback when symmetric memory is unavailable)
+    "halo"       banded matrices: only the needed column ranges are sent (5-pt Poisson 8192^2 on 8 GPUs: 2 x 64 KB per rank)
 
 Host logic only -- the local kernel is injected (`make_local_op`) so the world_size-2 gloo tests on CPU can drive the
 same code with the CPU oracle, while bench.py passes the sm_100a operator.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable
 
 import torch
@@ -32,13 +46,25 @@ def split_rows_by_nnz(off: torch.Tensor, world: int) -> torch.Tensor:
     return torch.cummax(b, 0).values
 
 
+def split_column_panels(off: torch.Tensor, col: torch.Tensor, val: torch.Tensor, lo: int, hi: int):
+    """(off, col, val) of the sub-matrices with columns inside / outside [lo, hi); row order and column order are kept."""
+    own = (col >= lo) & (col < hi)
+    cs = torch.zeros(col.numel() + 1, dtype=torch.int64, device=col.device)
+    cs[1:] = torch.cumsum(own.to(torch.int64), 0)
+    o64 = off.to(torch.int64) - off[0].to(torch.int64)
+    inside = cs[o64]
+    off_own = inside.to(torch.int32).contiguous()
+    off_rem = (o64 - inside).to(torch.int32).contiguous()
+    rem = ~own
+    return (off_own, col[own].contiguous(), val[own].contiguous()), (off_rem, col[rem].contiguous(), val[rem].contiguous())
+
+
 class ShardedCsr:
-    """This rank's row block of a global square CSR matrix plus the all-gather layout for x.
+    """This rank's row block of a global square CSR matrix plus the exchange plan for x.
 
     Two distributions, both fixed at set-up:
       * A and y by contiguous row blocks with ~nnz/G non-zeros each (rows [r0, r1) on this rank);
-      * x by EQUAL blocks of x_block = ceil(n/G) entries (the last one zero-padded), so the exchange step is one
-        all_gather_into_tensor of equal shards with no padding traffic, and the gathered vector is x itself:
+      * x by EQUAL blocks of x_block = ceil(n/G) entries (the last one zero-padded), so the assembled vector is x itself:
         column indices need no remapping.
     (In a solver loop y becomes the next x: with skewed matrices the two distributions differ and the hand-over is a
     redistribution of the row-block / equal-block overlap; for banded matrices they coincide up to a halo.)
@@ -46,7 +72,7 @@ class ShardedCsr:
 
     def __init__(self, off: torch.Tensor, col: torch.Tensor, val: torch.Tensor, rank: int, world: int,
                  make_local_op: Callable[[int, int, dict], Callable], group=None, base: int = 0, balance: str = "nnz",
-                 exchange: str = "auto"):
+                 exchange: str = "auto", overlap: bool = True):
         assert base == 0
         self.rank, self.world, self.group = rank, world, group
         n = off.numel() - 1
@@ -69,45 +95,108 @@ class ShardedCsr:
         self.nnz = n1 - n0
         self.cols_padded = world * self.x_block
         self.x_full = torch.zeros(self.cols_padded, dtype=val.dtype, device=val.device)
-        self.local_op = make_local_op(self.rows, self.cols_padded, dict(off=self.off, col=self.col, val=self.val))
+        self._step = 0
         self._plan_exchange(exchange)
+        # column panels: only where the whole x is exchanged and there is something to overlap with
+        self.panels = overlap and world > 1 and self.exchange in ("allgather", "p2p") and self.rows > 0
+        if self.panels:
+            lo = rank * self.x_block
+            (oo, oc, ov), (ro, rc, rv) = split_column_panels(self.off, self.col, self.val, lo, lo + self.x_block)
+            self.own_nnz, self.remote_nnz = int(oc.numel()), int(rc.numel())
+            self.own_op = make_local_op(self.rows, self.cols_padded, dict(off=oo, col=oc, val=ov))
+            self.remote_op = make_local_op(self.rows, self.cols_padded, dict(off=ro, col=rc, val=rv))
+            self.local_op = self.remote_op            # (kept for callers that close "the" local operator)
+        else:
+            self.local_op = make_local_op(self.rows, self.cols_padded, dict(off=self.off, col=self.col, val=self.val))
+        if self.exchange == "p2p":
+            self._init_p2p()
+        elif self.exchange == "allgather" and val.is_cuda and world > 1:
+            self.side = torch.cuda.Stream()
+            self.ev_in, self.ev_out = torch.cuda.Event(), torch.cuda.Event()
 
+    # ------------------------------------------------------------------------------------------------ planning
     def _plan_exchange(self, exchange: str):
         """Structure-only preprocessing of the exchange step: which part of x does this row block actually read?
 
         The local columns span [cmin, cmax].  For a banded matrix that is this rank's own block plus a halo (5-pt
-        Poisson 8192^2 on 8 GPUs: 2 x 64 KB instead of 470 MB), so instead of the full all-gather every rank receives,
+        Poisson 8192^2 on 8 GPUs: 2 x 64 KB instead of 470 MB), so instead of the whole x every rank receives,
         from each owner, only the overlap of [cmin, cmax] with the owner's x block -- straight into x_full, no packing.
-        Falls back to the all-gather when the ranks together need more than half of what the all-gather would move
-        (R-MAT: every rank reads every block)."""
+        Otherwise (R-MAT: every rank reads every block) the whole x is assembled: by peer copies out of symmetric memory
+        ("p2p") when that is available on CUDA, else by one NCCL all-gather."""
         world, blk = self.world, self.x_block
         self.recv_plan, self.send_plan, self.exchange = [], [], "allgather"
-        if world == 1 or exchange == "allgather":
+        if world == 1:
             return
-        if self.nnz > 0:
-            cmin, cmax = int(self.col.min().item()), int(self.col.max().item()) + 1
-        else:
-            cmin, cmax = 0, 0
-        need = torch.tensor([[cmin, cmax]], dtype=torch.int64, device=self.col.device)
-        allneed = [torch.zeros_like(need) for _ in range(world)]
-        dist.all_gather(allneed, need, group=self.group)
-        ranges = [tuple(int(v) for v in t.flatten().tolist()) for t in allneed]      # (cmin, cmax) of every rank
-        total = 0
-        for g, (lo_need, hi_need) in enumerate(ranges):
-            for h in range(world):
-                if h == g:
-                    continue
-                lo, hi = max(lo_need, h * blk), min(hi_need, (h + 1) * blk)
-                if hi > lo:
-                    total += hi - lo
-                    if g == self.rank:
-                        self.recv_plan.append((h, lo, hi))          # receive x[lo:hi] from its owner h
-                    if h == self.rank:
-                        self.send_plan.append((g, lo - h * blk, hi - h * blk))   # send my block[lo:hi] to g
-        if exchange == "halo" or total * 2 < world * (world - 1) * blk:
-            self.exchange = "halo"
-            self.exchanged_elements = total
+        if exchange in ("auto", "halo"):
+            if self.nnz > 0:
+                cmin, cmax = int(self.col.min().item()), int(self.col.max().item()) + 1
+            else:
+                cmin, cmax = 0, 0
+            need = torch.tensor([[cmin, cmax]], dtype=torch.int64, device=self.col.device)
+            allneed = [torch.zeros_like(need) for _ in range(world)]
+            dist.all_gather(allneed, need, group=self.group)
+            ranges = [tuple(int(v) for v in t.flatten().tolist()) for t in allneed]      # (cmin, cmax) of every rank
+            total = 0
+            for g, (lo_need, hi_need) in enumerate(ranges):
+                for h in range(world):
+                    if h == g:
+                        continue
+                    lo, hi = max(lo_need, h * blk), min(hi_need, (h + 1) * blk)
+                    if hi > lo:
+                        total += hi - lo
+                        if g == self.rank:
+                            self.recv_plan.append((h, lo, hi))          # receive x[lo:hi] from its owner h
+                        if h == self.rank:
+                            self.send_plan.append((g, lo - h * blk, hi - h * blk))   # send my block[lo:hi] to g
+            if exchange == "halo" or total * 2 < world * (world - 1) * blk:
+                self.exchange = "halo"
+                self.exchanged_elements = total
+                return
+        if exchange in ("auto", "p2p") and self.col.is_cuda and os.environ.get("B200SPMV_NO_P2P", "0") != "1":
+            self.exchange = "p2p"
 
+    def _init_p2p(self):
+        """x shards in symmetric memory (two of them: step k writes shard k & 1), peer views, copy streams.  Any failure
+        (no IPC support on the box, old driver) falls back to the NCCL all-gather -- decided collectively."""
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+            grp = self.group if self.group is not None else dist.group.WORLD
+            self.sym = [symm.empty(self.x_block, dtype=self.val.dtype, device=self.val.device) for _ in range(2)]
+            self.hdl = [symm.rendezvous(t, group=grp) for t in self.sym]
+            self.peer = [[h.get_buffer(r, (self.x_block,), self.val.dtype) for r in range(self.world)] for h in self.hdl]
+            for t in self.sym:
+                t.zero_()
+        except Exception as e:  # pragma: no cover (GPU boxes only)
+            self.p2p_error = repr(e)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.val.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self.exchange = "allgather"
+            self.side = torch.cuda.Stream()
+            self.ev_in, self.ev_out = torch.cuda.Event(), torch.cuda.Event()
+            return
+        ncs = min(3, self.world - 1)
+        self.copy_streams = [torch.cuda.Stream() for _ in range(ncs)]
+        self.ev_ready = torch.cuda.Event()
+        self.ev_done = [torch.cuda.Event() for _ in range(ncs)]
+        self.pull_order = [(self.rank + 1 + i) % self.world for i in range(self.world - 1)]   # staggered: no source read twice at once
+
+    def describe_exchange(self) -> str:
+        if self.world == 1:
+            return "none (single GPU)"
+        if self.exchange == "halo":
+            return f"halo exchange: {self.exchanged_elements * self.val.element_size()} B per step over all ranks (batch_isend_irecv)"
+        how = {"p2p": "x shards in symmetric memory; one device-side barrier, then copy-engine peer copies over NVLink on side streams "
+                      "(double-buffered shards)",
+               "allgather": "one NCCL all_gather_into_tensor on a side stream"}[self.exchange]
+        if self.panels:
+            how += (f"; overlapped with the own-column panel of the local product ({self.own_nnz} of {self.nnz} local non-zeros), "
+                    "the remote-column panel follows with beta = 1")
+        return how
+
+    # ------------------------------------------------------------------------------------------------ exchange
     def _halo_exchange(self, x_shard: torch.Tensor):
         blk = self.x_block
         self.x_full[self.rank * blk:(self.rank + 1) * blk].copy_(x_shard)
@@ -116,6 +205,45 @@ class ShardedCsr:
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+
+    def _start_exchange(self, x_shard: torch.Tensor):
+        """Kick off the assembly of x_full; returns a function that makes the current stream wait for it."""
+        blk = self.x_block
+        own = self.x_full[self.rank * blk:(self.rank + 1) * blk]
+        if self.exchange == "p2p":
+            i = self._step & 1
+            self._step += 1
+            self.sym[i].copy_(x_shard)
+            own.copy_(x_shard)
+            self.hdl[i].barrier(channel=0, timeout_ms=20000)     # every rank's shard i is written (and step k-1 is fully read)
+            main = torch.cuda.current_stream()
+            self.ev_ready.record(main)
+            for s in self.copy_streams:
+                s.wait_event(self.ev_ready)
+            ncs = len(self.copy_streams)
+            for k, h in enumerate(self.pull_order):
+                with torch.cuda.stream(self.copy_streams[k % ncs]):
+                    self.x_full[h * blk:(h + 1) * blk].copy_(self.peer[i][h], non_blocking=True)
+            for s, e in zip(self.copy_streams, self.ev_done):
+                e.record(s)
+
+            def wait():
+                for e in self.ev_done:
+                    main.wait_event(e)
+            return wait
+        if self.exchange == "allgather" and hasattr(self, "side"):
+            main = torch.cuda.current_stream()
+            own.copy_(x_shard)
+            self.ev_in.record(main)
+            self.side.wait_event(self.ev_in)
+            with torch.cuda.stream(self.side):
+                dist.all_gather_into_tensor(self.x_full, x_shard, group=self.group)
+                self.ev_out.record(self.side)
+            return lambda: main.wait_event(self.ev_out)
+        # CPU (gloo tests) / no side stream: blocking exchange
+        own.copy_(x_shard)
+        dist.all_gather_into_tensor(self.x_full, x_shard, group=self.group)
+        return lambda: None
 
     def new_x_shard(self, x=None):
         """This rank's equal block of a global vector x (zero-padded at the end of the last block)."""
@@ -135,19 +263,54 @@ class ShardedCsr:
         return t
 
     def gather_x(self, x_shard: torch.Tensor) -> torch.Tensor:
-        """The path's single exchange step: all-gather of the equal x shards, or -- when the set-up analysis found that
-        this matrix only reads a narrow column range per rank -- just the needed ranges (halo exchange)."""
+        """The path's single exchange step, complete on return (stream order): x_full holds everything this rank reads."""
         if self.world == 1:
             self.x_full[:self.x_block].copy_(x_shard)
         elif self.exchange == "halo":
             self._halo_exchange(x_shard)
         else:
-            dist.all_gather_into_tensor(self.x_full, x_shard, group=self.group)
+            self._start_exchange(x_shard)()
         return self.x_full
 
     def spmv(self, x_shard: torch.Tensor, y_shard: torch.Tensor, alpha=1.0, beta=0.0) -> torch.Tensor:
         """y_shard = alpha * A[r0:r1, :] @ x + beta * y_shard   (x given as this rank's equal block)."""
-        self.gather_x(x_shard)
-        if self.rows > 0:
-            self.local_op(self.x_full, y_shard, alpha, beta)
+        if not self.panels:
+            self.gather_x(x_shard)
+            if self.rows > 0:
+                self.local_op(self.x_full, y_shard, alpha, beta)
+            return y_shard
+        wait = self._start_exchange(x_shard)
+        self.own_op(self.x_full, y_shard, alpha, beta)            # needs only this rank's own x block
+        wait()
+        self.remote_op(self.x_full, y_shard, alpha, 1.0)
         return y_shard
+
+    def make_step(self, x_shard: torch.Tensor, y_shard: torch.Tensor, local_call=None):
+        """A zero-argument callable for timing loops: one full step y = A x with fixed buffers and alpha = 1, beta = 0;
+        uses the operators' prebuilt calls when they offer them (ctypes arguments built once)."""
+        if not self.panels:
+            call = local_call
+            if call is None:
+                op = self.local_op
+                call = op.prebuilt(self.x_full, y_shard, 1.0, 0.0) if hasattr(op, "prebuilt") else (lambda: op(self.x_full, y_shard, 1.0, 0.0))
+
+            def step():
+                self.gather_x(x_shard)
+                call()
+            return step
+        mk = lambda op, beta: (op.prebuilt(self.x_full, y_shard, 1.0, beta) if hasattr(op, "prebuilt")
+                               else (lambda: op(self.x_full, y_shard, 1.0, beta)))
+        own_call, remote_call = mk(self.own_op, 0.0), mk(self.remote_op, 1.0)
+
+        def step():
+            wait = self._start_exchange(x_shard)
+            own_call()
+            wait()
+            remote_call()
+        return step
+
+    def close(self):
+        for name in ("own_op", "remote_op", "local_op"):
+            op = getattr(self, name, None)
+            if op is not None and hasattr(op, "close"):
+                op.close()

@@ -75,6 +75,14 @@ B200SPMV_EXPORT int    b200spmv_csr_flat_mv(void* stream, int dtype, int64_t row
 B200SPMV_EXPORT void   b200spmv_csr_flat_plan_offsets(int64_t rows, int64_t nnz, size_t* endmask, size_t* chunk_run,
                                                       size_t* nzrow, size_t* ctl);
 
+/* CSR x dense: C = alpha*A*B + beta*C, A rows x cols (CSR, int32 indices), B cols x n, C rows x n, each dense matrix row- or
+ * column-major with leading dimension ld* (elements).  Replaces cusparseSpMM for CSR descriptors, opA = opB = NON_TRANSPOSE
+ * (cuSPARSE/spmm_csr/spmm_csr_example.c:105-132).  No workspace. */
+B200SPMV_EXPORT int b200spmm_csr(void* stream, int dtype, int64_t rows, int64_t cols, int64_t n, int64_t nnz,
+                                 const void* row_offsets, const void* col_ind, const void* values, int32_t base,
+                                 const void* alpha, const void* beta, int scalars_on_device, const void* B, int64_t ldb,
+                                 int b_row_major, void* C, int64_t ldc, int c_row_major);
+
 /* COO (row-sorted or not).  Replaces cusparseSpMV for cusparseCreateCoo descriptors
  * (cuSPARSE/spmv_coo/spmv_coo_example.c:86-104). */
 B200SPMV_EXPORT size_t b200spmv_coo_workspace_bytes(int64_t rows, int64_t nnz);
@@ -169,6 +177,17 @@ B200SPMV_EXPORT cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t, cuspa
 B200SPMV_EXPORT cusparseStatus_t cusparseSpMV(cusparseHandle_t, cusparseOperation_t, const void*, cusparseConstSpMatDescr_t,
                                               cusparseConstDnVecDescr_t, const void*, cusparseDnVecDescr_t, cudaDataType,
                                               cusparseSpMVAlg_t, void*);
+/* cusparse.h:5862-5898 -- spmm_csr_example.c:105-132 (dense-matrix descriptors stay with the real library: the shim reads
+ * them through cusparseConstDnMatGet, so cusparseCreateDnMat / cusparseDestroyDnMat need no re-export) */
+B200SPMV_EXPORT cusparseStatus_t cusparseSpMM_bufferSize(cusparseHandle_t, cusparseOperation_t, cusparseOperation_t, const void*,
+                                                         cusparseConstSpMatDescr_t, cusparseConstDnMatDescr_t, const void*,
+                                                         cusparseDnMatDescr_t, cudaDataType, cusparseSpMMAlg_t, size_t*);
+B200SPMV_EXPORT cusparseStatus_t cusparseSpMM_preprocess(cusparseHandle_t, cusparseOperation_t, cusparseOperation_t, const void*,
+                                                         cusparseConstSpMatDescr_t, cusparseConstDnMatDescr_t, const void*,
+                                                         cusparseDnMatDescr_t, cudaDataType, cusparseSpMMAlg_t, void*);
+B200SPMV_EXPORT cusparseStatus_t cusparseSpMM(cusparseHandle_t, cusparseOperation_t, cusparseOperation_t, const void*,
+                                              cusparseConstSpMatDescr_t, cusparseConstDnMatDescr_t, const void*,
+                                              cusparseDnMatDescr_t, cudaDataType, cusparseSpMMAlg_t, void*);
 #ifdef __cplusplus
 }
 #endif

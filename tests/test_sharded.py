@@ -37,6 +37,8 @@ def _worker(rank, world, port, rows, q):
         y0 = torch.from_numpy(O.uniform(6, rows))
         sh = ShardedCsr(off, col, val, rank, world, _oracle_op)
         assert sh.exchange == "allgather"                  # R-MAT: every rank reads every x block
+        assert sh.panels and sh.own_nnz + sh.remote_nnz == sh.nnz   # local matrix split into own-column / remote-column panels
+        assert "overlapped with the own-column panel" in sh.describe_exchange()
         xs, ys = sh.new_x_shard(x), sh.new_y_shard(y0)
         sh.spmv(xs, ys, alpha=-1.0, beta=1.0)
         # second product chained on the first (solver style: y becomes the next x -> redistribute row blocks into
@@ -54,6 +56,22 @@ def _worker(rank, world, port, rows, q):
             q.put(out)
     finally:
         dist.destroy_process_group()
+
+
+def test_column_panels_partition_the_local_matrix():
+    from cudalibrarysamples_b200.sharded import split_column_panels
+    off, col, val = (torch.from_numpy(a) for a in O.rmat_csr(3000, avg_nnz=8, seed=9, val_seed=10))
+    x, y0 = O.uniform(1, 3000), O.uniform(2, 3000)
+    lo, hi = 1000, 2000
+    (oo, oc, ov), (ro, rc, rv) = split_column_panels(off, col, val, lo, hi)
+    assert oc.numel() + rc.numel() == col.numel()
+    assert bool(((oc >= lo) & (oc < hi)).all()) and bool(((rc < lo) | (rc >= hi)).all())
+    assert int(oo[-1]) == oc.numel() and int(ro[-1]) == rc.numel() and int(oo[0]) == 0 and int(ro[0]) == 0
+    # own panel first (beta as given), remote panel second with beta = 1: the same product
+    y = O.spmv_csr(oo.numpy(), oc.numpy(), ov.numpy(), x, y0, -0.5, 2.0)
+    y = O.spmv_csr(ro.numpy(), rc.numpy(), rv.numpy(), x, y, -0.5, 1.0)
+    want = O.spmv_csr(off.numpy(), col.numpy(), val.numpy(), x, y0, -0.5, 2.0)
+    assert np.linalg.norm(y - want) <= 1e-13 * np.linalg.norm(want)
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -79,9 +97,10 @@ def test_sharded_spmv_matches_single_process(world):
         assert a["r1"] == b["r0"]
     got_y = np.concatenate([d["y"] for d in out])
     got_z = np.concatenate([d["z"] for d in out])
-    assert np.array_equal(got_y, y)          # same oracle arithmetic per row -> bit-identical
-    assert np.array_equal(got_z, z)
-    assert np.array_equal(out[0]["xg"], y)   # the last gather carried y, reassembled from equal blocks
+    # every row is summed in two column panels (own block first, the rest with beta = 1): equal up to rounding
+    assert np.linalg.norm(got_y - y) <= 1e-14 * np.linalg.norm(y)
+    assert np.linalg.norm(got_z - z) <= 1e-13 * np.linalg.norm(z)
+    assert np.array_equal(out[0]["xg"], got_y)   # the last gather carried y, reassembled bit for bit from equal blocks
     assert all(d["x_block"] == (rows + world - 1) // world for d in out)
     nnzs = [d["nnz"] for d in out]
     assert sum(nnzs) == off[-1]
