@@ -533,7 +533,7 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
         const bool trusted = plan_is_trusted(m, externalBuffer);
         if (trusted && m.use_flat) {
             logf("SpMV csr_flat_kernel", m);
-            rc = b200spmv_csr_flat_mv((void*)stream, dt, m.rows, m.cols, m.nnz, m.col_ind, m.values, (int32_t)m.base, alpha, beta,
+            rc = b200spmv_csr_flat_mv((void*)stream, dt, m.rows, m.cols, m.nnz, m.offsets, m.col_ind, m.values, (int32_t)m.base, alpha, beta,
                                       on_dev, x.values, (void*)y.values, (char*)externalBuffer + flat_plan_offset(m));
             b200::stats().native_calls++;
             return to_status(rc);

@@ -15,9 +15,9 @@
 //     x gathered through L1 (the kernel uses ~100 B of shared memory, so the whole unified L1 serves x: the gather-only
 //     rate drops from 1.26 to 0.95 elements/clk/SM when 100 KB of it is carved out, scripts/micro_gather.cu), a step of 32
 //     non-zeros inside one row costs one add; a step with row ends costs one butterfly + a segmented shuffle scan with as
-//     many levels as its longest remaining segment; the end lanes look their rows up in nzrow, store y and fill the empty
-//     rows in front of them (y = beta*y).  Rows crossing a warp chunk are stitched per CTA (one thread, fixed order), rows
-//     crossing a CTA (2048 non-zeros) by csr_flat_fixup_kernel in CTA order: bit-reproducible, no atomics.
+//     many levels as its longest remaining segment; the end lanes look their rows up in nzrow and store y.  Rows crossing
+//     a warp chunk are stitched per CTA (the last warp to finish, fixed order), rows crossing a CTA (2048 non-zeros) and the
+//     EMPTY rows (y = beta*y) by the small csr_flat_fixup_kernel launch that follows: bit-reproducible, no atomics.
 //
 // Replaces cusparse::csrmv_v3_kernel behind cusparseSpMV for preprocessed CSR descriptors (call sites:
 // cuSPARSE/spmv_csr/spmv_csr_example.c:104-112, cuSOLVERSp2cuDSS/csreigvsi2cuDSS_double.cpp:148-150,221).
@@ -35,10 +35,15 @@ namespace b200 {
 #endif
 constexpr int FLAT_STEPS = 8;                      // 32-element steps per warp chunk
 constexpr int FLAT_CHUNK = 32 * FLAT_STEPS;        // 256 non-zeros per warp
-constexpr int FLAT_WARPS = 8;
+#ifndef B200_FLAT_WARPS
+#define B200_FLAT_WARPS 8
+#endif
+constexpr int FLAT_WARPS = B200_FLAT_WARPS;         // warp chunks stitched per CTA (a divisor of 8)
 constexpr int FLAT_BLOCK = 32 * FLAT_WARPS;
 constexpr int FLAT_CTA_NNZ = FLAT_CHUNK * FLAT_WARPS;   // 2048 non-zeros per CTA
 constexpr int FLAT_CTA_WORDS = FLAT_CTA_NNZ / 32;
+constexpr int FLAT_PAD_NNZ = 2048;                 // the plan arrays are padded to this many non-zeros (independent of FLAT_WARPS)
+static_assert(FLAT_PAD_NNZ % FLAT_CTA_NNZ == 0, "FLAT_WARPS must divide 8");
 constexpr int FLAT_BATCH = B200_FLAT_BATCH;
 constexpr int SCAN_ITEMS = 2048;                   // items per block of the preprocessing scans
 static_assert(FLAT_STEPS % FLAT_BATCH == 0, "steps per chunk must be a multiple of the batch");
@@ -56,13 +61,15 @@ struct FlatPlan {
 
 static inline size_t flat_align(size_t v) { return (v + 255) / 256 * 256; }
 static inline int64_t flat_num_ctas(int64_t nnz) { return (nnz + FLAT_CTA_NNZ - 1) / FLAT_CTA_NNZ; }
+static inline int64_t flat_num_chunks_padded(int64_t nnz) { return (nnz + FLAT_PAD_NNZ - 1) / FLAT_PAD_NNZ * (FLAT_PAD_NNZ / FLAT_CHUNK); }
 
 static size_t flat_layout(int64_t rows, int64_t nnz, void* ws, FlatPlan* p) {
-    const size_t nctas = (size_t)flat_num_ctas(nnz);
-    const size_t nscan = (size_t)((rows > (int64_t)nctas * FLAT_WARPS ? rows : (int64_t)nctas * FLAT_WARPS) / SCAN_ITEMS + 2);
+    const size_t nchunks = (size_t)flat_num_chunks_padded(nnz);
+    const size_t nctas = nchunks;                                  // upper bound for every FLAT_WARPS (one CTA per chunk)
+    const size_t nscan = (size_t)((rows > (int64_t)nchunks ? rows : (int64_t)nchunks) / SCAN_ITEMS + 2);
     size_t o = 0;
-    const size_t o_mask = o;  o = flat_align(o + nctas * FLAT_CTA_WORDS * sizeof(unsigned));
-    const size_t o_crun = o;  o = flat_align(o + (nctas * FLAT_WARPS + 1) * sizeof(int));
+    const size_t o_mask = o;  o = flat_align(o + nchunks * FLAT_STEPS * sizeof(unsigned));
+    const size_t o_crun = o;  o = flat_align(o + (nchunks + 1) * sizeof(int));
     const size_t o_nzr  = o;  o = flat_align(o + ((size_t)rows + 2) * sizeof(int));
     const size_t o_cf   = o;  o = flat_align(o + nctas * sizeof(double));
     const size_t o_cl   = o;  o = flat_align(o + nctas * sizeof(double));
@@ -212,6 +219,7 @@ __global__ void flat_finish_kernel(FlatPlan p, int64_t rows, int64_t nchunks, in
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 struct FlatArgs {
+    const int* off;
     const int* col;
     const T*   val;
     const T*   x;
@@ -228,6 +236,14 @@ __device__ __forceinline__ T flat_allsum(T v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// y[r] = alpha * v + beta * y[r]; beta == 0 never reads y (predicated load, no branch)
+template <typename T>
+__device__ __forceinline__ void flat_store_y(T* yp, T alpha, T v, T beta) {
+    T old = T(0);
+    if (beta != T(0)) old = *yp;
+    *yp = alpha * v + beta * old;
 }
 
 template <typename T>
@@ -250,7 +266,6 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
         const int n0 = (int)c0, n1 = min(n0 + FLAT_CHUNK, a.nnz);
         const unsigned mreg = lane < FLAT_STEPS ? __ldg(a.plan.endmask + c * FLAT_STEPS + lane) : 0u;
         int run = __ldg(a.plan.chunk_run + c);             // rows that ended before this chunk
-        const int nruns = __ldg(a.plan.ctl);
         const int* colp = a.col + n0;
         const T*   valp = a.val + n0;
         const T*   xp = a.x - a.base;
@@ -266,28 +281,26 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
             }
         };
         issue(0);
-        // Run-time loops over the steps: with everything unrolled the kernel was 106 KB of SASS and stalled on instruction
-        // fetch (ncu: "no instruction" the top stall reason, 160 us); only the short load / gather loops stay unrolled.
-#pragma unroll 1
+        // Unrolled over the 8 steps (static register indexing, no loop control), but the scan inside a flush is a run-time
+        // loop: with everything unrolled the kernel was 106 KB of SASS and stalled on instruction fetch (160 us); with
+        // run-time step loops it was 20 KB but executed 61 M instructions, 45 % of them select chains / loop control (109 us).
+#pragma unroll
         for (int kb = 0; kb < FLAT_STEPS; kb += FLAT_BATCH) {
             if (n0 + kb * 32 >= n1) break;                 // warp-uniform: the matrix' last chunk may be short
             T p[FLAT_BATCH];
 #pragma unroll
             for (int k = 0; k < FLAT_BATCH; k++) p[k] = (n0 + (kb + k) * 32 + lane < n1) ? vv[k] * __ldg(xp + cc[k]) : T(0);
             if (kb + FLAT_BATCH < FLAT_STEPS && n0 + (kb + FLAT_BATCH) * 32 < n1) issue(kb + FLAT_BATCH);
-#pragma unroll 1
+#pragma unroll
             for (int k = 0; k < FLAT_BATCH; k++) {
                 const unsigned m = __shfl_sync(0xffffffffu, mreg, kb + k);
-                T pk = p[0];                               // p[k] with a run-time k: a select chain, not local memory
-#pragma unroll
-                for (int jj = 1; jj < FLAT_BATCH; jj++) pk = k == jj ? p[jj] : pk;
+                const T pk = p[k];
                 if (m == 0u) { acc += pk; continue; }      // the whole step lies inside one row
                 const int e1 = __ffs(m) - 1, ek = 31 - __clz(m);
                 // my row (if I end one): issued first, the look-up's latency hides behind the shuffles below
                 const bool is_end = (m >> lane) & 1u;
-                const int  j = run + __popc(m & ((1u << lane) - 1u));        // index of the row (among non-empty rows) I end
-                int rlo = 0, row = 0;
-                if (is_end) { rlo = __ldg(a.plan.nzrow + j); row = __ldg(a.plan.nzrow + j + 1); }
+                int row = 0;
+                if (is_end) row = __ldg(a.plan.nzrow + run + __popc(m & ((1u << lane) - 1u)) + 1);   // (run + k)-th non-empty row
                 const T t1 = flat_allsum(acc + (lane <= e1 ? pk : T(0)));
                 T q = (lane > e1 && lane <= ek) ? pk : T(0);
                 if (m & (m - 1u)) {                        // more rows end: segmented inclusive scan
@@ -301,30 +314,13 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
                     }
                 }
                 const T res = lane == e1 ? t1 : q;
+                bool mine = is_end;
                 if (frow < 0) {                            // the chunk's first row end goes to the stitch
                     first = __shfl_sync(0xffffffffu, res, e1);
                     frow = __shfl_sync(0xffffffffu, row, e1);
-                    if (is_end && lane != e1) { T* yp = a.y + row; *yp = axpby(alpha, res, beta, yp); }
-                } else if (is_end) {
-                    T* yp = a.y + row;
-                    *yp = axpby(alpha, res, beta, yp);
+                    mine = is_end && lane != e1;
                 }
-                // empty rows in front of my row: y = beta * y (short gaps by the lane itself, long ones by the whole warp)
-                const int glen = is_end ? row - rlo - 1 : 0;
-                if (glen > 0 && glen < 16)
-                    for (int r = rlo + 1; r < row; r++) { T* yp = a.y + r; *yp = axpby(alpha, T(0), beta, yp); }
-                unsigned big = __ballot_sync(0xffffffffu, glen >= 16);
-                while (big) {
-                    const int src = __ffs(big) - 1;
-                    big &= big - 1u;
-                    const int lo = __shfl_sync(0xffffffffu, rlo, src), hi = __shfl_sync(0xffffffffu, row, src);
-                    for (int r = lo + 1 + lane; r < hi; r += 32) { T* yp = a.y + r; *yp = axpby(alpha, T(0), beta, yp); }
-                }
-                const unsigned fin = __ballot_sync(0xffffffffu, is_end && j == nruns - 1);   // the matrix' last non-empty row
-                if (fin) {
-                    const int lo = __shfl_sync(0xffffffffu, row, __ffs(fin) - 1);
-                    for (int r = lo + 1 + lane; r < a.rows; r += 32) { T* yp = a.y + r; *yp = axpby(alpha, T(0), beta, yp); }
-                }
+                if (mine) flat_store_y(a.y + row, alpha, res, beta);
                 run += __popc(m);
                 acc = lane > ek ? pk : T(0);
             }
@@ -355,7 +351,7 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
             if (fr >= 0) {
                 const T tot = running + sFirst[w];
                 if (!has && !starts_row) a.plan.cta_first[cta] = (double)tot;            // the row began in an earlier CTA
-                else { T* yp = a.y + fr; *yp = axpby(alpha, tot, beta, yp); }
+                else flat_store_y(a.y + fr, alpha, tot, beta);
                 running = sLast[w];
                 has = true;
             } else {
@@ -368,10 +364,15 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
     }
 }
 
-// rows that cross CTA borders: thread t owns the row that STARTS in CTA t and runs past its end
+// Second (small) launch: (1) rows that cross CTA borders -- thread t owns the row that STARTS in CTA t and runs past its
+// end, partials added in CTA order; (2) EMPTY rows, which the main kernel never sees: y = beta * y, one thread per row.
 template <typename T>
 __global__ void __launch_bounds__(256) csr_flat_fixup_kernel(const FlatArgs<T> a, long long nctas) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const T alpha = a.s.a(), beta = a.s.b();
+    if (t < a.rows) {
+        if (__ldg(a.off + t) == __ldg(a.off + t + 1)) flat_store_y(a.y + t, alpha, T(0), beta);
+    }
     if (t >= nctas - 1) return;
     const bool tail_open = !(__ldg(a.plan.endmask + (t + 1) * FLAT_CTA_WORDS - 1) >> 31);
     if (!tail_open) return;
@@ -383,8 +384,7 @@ __global__ void __launch_bounds__(256) csr_flat_fixup_kernel(const FlatArgs<T> a
     while (__ldcg(a.plan.cta_flags + u) == 0) { sum += __ldcg(a.plan.cta_first + u); u++; }
     sum += __ldcg(a.plan.cta_first + u);
     const int row = __ldg(a.plan.nzrow + __ldg(a.plan.chunk_run + u * FLAT_WARPS) + 1);
-    T* yp = a.y + row;
-    *yp = axpby(a.s.a(), (T)sum, a.s.b(), yp);
+    flat_store_y(a.y + row, alpha, (T)sum, beta);
 }
 
 template <typename T>
@@ -395,10 +395,10 @@ __global__ void flat_scale_y_kernel(T* __restrict__ y, int64_t rows, Scalars<T> 
 }
 
 template <typename T>
-static int launch_flat(cudaStream_t stream, int64_t rows, int64_t nnz, const void* col, const void* val, int base,
+static int launch_flat(cudaStream_t stream, int64_t rows, int64_t nnz, const void* off, const void* col, const void* val, int base,
                        const void* alpha, const void* beta, int on_device, const void* x, void* y, void* ws) {
     FlatArgs<T> a;
-    a.col = (const int*)col; a.val = (const T*)val; a.x = (const T*)x; a.y = (T*)y;
+    a.off = (const int*)off; a.col = (const int*)col; a.val = (const T*)val; a.x = (const T*)x; a.y = (T*)y;
     a.base = base; a.rows = (int)rows; a.nnz = (int)nnz;
     if (on_device) { a.s.alpha = T(0); a.s.beta = T(0); a.s.alpha_dev = (const T*)alpha; a.s.beta_dev = (const T*)beta; }
     else { a.s.alpha = *(const T*)alpha; a.s.beta = *(const T*)beta; a.s.alpha_dev = nullptr; a.s.beta_dev = nullptr; }
@@ -413,8 +413,9 @@ static int launch_flat(cudaStream_t stream, int64_t rows, int64_t nnz, const voi
     const int64_t nctas = flat_num_ctas(nnz);
     csr_flat_kernel<T><<<(unsigned)nctas, FLAT_BLOCK, 0, stream>>>(a);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || nctas < 2) return (int)e;
-    csr_flat_fixup_kernel<T><<<(unsigned)((nctas - 1 + 255) / 256), 256, 0, stream>>>(a, (long long)nctas);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t work = rows > nctas - 1 ? rows : nctas - 1;                    // empty rows + CTA-crossing rows
+    csr_flat_fixup_kernel<T><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(a, (long long)nctas);
     return (int)cudaGetLastError();
 }
 
@@ -435,8 +436,8 @@ int b200spmv_csr_flat_analyze(void* stream_, int64_t rows, int64_t nnz, const vo
     FlatPlan p;
     const size_t total = flat_layout(rows, nnz, workspace, &p);
     (void)total;
-    const int64_t nctas = flat_num_ctas(nnz), nchunks = nctas * FLAT_WARPS, nwords = (nnz + 31) / 32;
-    cudaError_t e = cudaMemsetAsync(p.endmask, 0, (size_t)nctas * FLAT_CTA_WORDS * sizeof(unsigned), stream);
+    const int64_t nchunks = flat_num_chunks_padded(nnz), nwords = (nnz + 31) / 32;
+    cudaError_t e = cudaMemsetAsync(p.endmask, 0, (size_t)nchunks * FLAT_STEPS * sizeof(unsigned), stream);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(p.ctl, 0, 64, stream);
     if (e != cudaSuccess) return (int)e;
@@ -476,16 +477,16 @@ void b200spmv_csr_flat_plan_offsets(int64_t rows, int64_t nnz, size_t* endmask, 
     if (ctl) *ctl = (size_t)((char*)p.ctl - (char*)nullptr);
 }
 
-int b200spmv_csr_flat_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz, const void* col_ind,
-                         const void* values, int32_t base, const void* alpha, const void* beta, int scalars_on_device,
-                         const void* x, void* y, void* workspace) {
+int b200spmv_csr_flat_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz, const void* row_offsets,
+                         const void* col_ind, const void* values, int32_t base, const void* alpha, const void* beta,
+                         int scalars_on_device, const void* x, void* y, void* workspace) {
     if (rows < 0 || cols < 0 || nnz < 0 || !alpha || !beta) return -1;
     if (rows == 0) return 0;
-    if (!y || !workspace || (nnz > 0 && (!col_ind || !values || !x))) return -1;
+    if (!y || !workspace || !row_offsets || (nnz > 0 && (!col_ind || !values || !x))) return -1;
     if (dtype == 0)
-        return launch_flat<float>((cudaStream_t)stream, rows, nnz, col_ind, values, base, alpha, beta, scalars_on_device, x, y, workspace);
+        return launch_flat<float>((cudaStream_t)stream, rows, nnz, row_offsets, col_ind, values, base, alpha, beta, scalars_on_device, x, y, workspace);
     if (dtype == 1)
-        return launch_flat<double>((cudaStream_t)stream, rows, nnz, col_ind, values, base, alpha, beta, scalars_on_device, x, y, workspace);
+        return launch_flat<double>((cudaStream_t)stream, rows, nnz, row_offsets, col_ind, values, base, alpha, beta, scalars_on_device, x, y, workspace);
     return -1;
 }
 

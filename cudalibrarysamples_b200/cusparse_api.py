@@ -38,6 +38,9 @@ CUSPARSE_SPMV_COO_ALG2 = 4
 CUSPARSE_SPMV_SELL_ALG1 = 5
 CUDA_R_32F = 0
 CUDA_R_64F = 1
+CUSPARSE_ORDER_COL = 1
+CUSPARSE_ORDER_ROW = 2
+CUSPARSE_SPMM_ALG_DEFAULT = 0
 
 _VT = {torch.float32: CUDA_R_32F, torch.float64: CUDA_R_64F}
 _IT = {torch.int32: CUSPARSE_INDEX_32I, torch.int64: CUSPARSE_INDEX_64I}
@@ -158,6 +161,39 @@ class Api:
     def cusparseDnVecSetValues(self, d, values):
         self._call(self.lib, "cusparseDnVecSetValues", d, _ptr(values))
 
+    # dense matrices: the descriptors always belong to the real library (the shim reads them through cusparseConstDnMatGet)
+    def cusparseCreateDnMat(self, rows, cols, ld, values, order=CUSPARSE_ORDER_COL):
+        d = C.c_void_p()
+        self._call(self.real, "cusparseCreateDnMat", C.byref(d), C.c_int64(rows), C.c_int64(cols), C.c_int64(ld), _ptr(values),
+                   C.c_int(_VT[values.dtype]), C.c_int(order))
+        return d
+
+    def cusparseDestroyDnMat(self, d):
+        self._call(self.real, "cusparseDestroyDnMat", d)
+
+    def cusparseSpMM_bufferSize(self, handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg=CUSPARSE_SPMM_ALG_DEFAULT):
+        dt = torch.float32 if computeType == CUDA_R_32F else torch.float64
+        pa, _ka = self._scalar(alpha, dt)
+        pb, _kb = self._scalar(beta, dt)
+        size = C.c_size_t(0)
+        self._call(self.lib, "cusparseSpMM_bufferSize", handle, C.c_int(opA), C.c_int(opB), pa, matA, matB, pb, matC,
+                   C.c_int(computeType), C.c_int(alg), C.byref(size))
+        return int(size.value)
+
+    def cusparseSpMM_preprocess(self, handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg, externalBuffer):
+        dt = torch.float32 if computeType == CUDA_R_32F else torch.float64
+        pa, _ka = self._scalar(alpha, dt)
+        pb, _kb = self._scalar(beta, dt)
+        self._call(self.lib, "cusparseSpMM_preprocess", handle, C.c_int(opA), C.c_int(opB), pa, matA, matB, pb, matC,
+                   C.c_int(computeType), C.c_int(alg), _ptr(externalBuffer))
+
+    def cusparseSpMM(self, handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg, externalBuffer):
+        dt = torch.float32 if computeType == CUDA_R_32F else torch.float64
+        pa, _ka = self._scalar(alpha, dt)
+        pb, _kb = self._scalar(beta, dt)
+        self._call(self.lib, "cusparseSpMM", handle, C.c_int(opA), C.c_int(opB), pa, matA, matB, pb, matC,
+                   C.c_int(computeType), C.c_int(alg), _ptr(externalBuffer))
+
     def cusparseCsrSetPointers(self, d, off, col, val):
         self._call(self.lib, "cusparseCsrSetPointers", d, _ptr(off), _ptr(col), _ptr(val))
 
@@ -277,3 +313,30 @@ class SpMVOperator:
             self.close()
         except Exception:
             pass
+
+
+def spmm(api: Api, rows: int, cols: int, arrays: dict, B: torch.Tensor, C0: torch.Tensor, alpha=1.0, beta=0.0,
+         order_b: int = CUSPARSE_ORDER_COL, order_c: int = CUSPARSE_ORDER_COL, base: int = 0) -> torch.Tensor:
+    """The call sequence of cuSPARSE/spmm_csr/spmm_csr_example.c:86-132 once: C = alpha*A*B + beta*C0.
+
+    B and C0 are 1-D device buffers holding the cols x n / rows x n matrices in the given order with the tight leading
+    dimension (column-major: ld = rows of the matrix; row-major: ld = n).  Returns the C buffer."""
+    val = arrays["val"]
+    n = B.numel() // max(cols, 1)
+    ct = _VT[val.dtype]
+    h = api.cusparseCreate()
+    matA = api.cusparseCreateCsr(rows, cols, int(arrays["col"].numel()), arrays["off"], arrays["col"], val, base)
+    Cb = C0.clone()
+    matB = api.cusparseCreateDnMat(cols, n, cols if order_b == CUSPARSE_ORDER_COL else n, B, order_b)
+    matC = api.cusparseCreateDnMat(rows, n, rows if order_c == CUSPARSE_ORDER_COL else n, Cb, order_c)
+    op = CUSPARSE_OPERATION_NON_TRANSPOSE
+    size = api.cusparseSpMM_bufferSize(h, op, op, alpha, matA, matB, beta, matC, ct)
+    buf = torch.empty(max(size, 16), dtype=torch.uint8, device=val.device)
+    api.cusparseSpMM_preprocess(h, op, op, alpha, matA, matB, beta, matC, ct, CUSPARSE_SPMM_ALG_DEFAULT, buf)
+    api.cusparseSpMM(h, op, op, alpha, matA, matB, beta, matC, ct, CUSPARSE_SPMM_ALG_DEFAULT, buf)
+    torch.cuda.synchronize()
+    api.cusparseDestroySpMat(matA)
+    api.cusparseDestroyDnMat(matB)
+    api.cusparseDestroyDnMat(matC)
+    api.cusparseDestroy(h)
+    return Cb

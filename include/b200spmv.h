@@ -66,11 +66,11 @@ B200SPMV_EXPORT size_t b200spmv_csr_flat_workspace_bytes(int64_t rows, int64_t n
 B200SPMV_EXPORT int    b200spmv_csr_flat_analyze(void* stream, int64_t rows, int64_t nnz, const void* row_offsets,
                                                  int32_t base, void* workspace);
 B200SPMV_EXPORT int    b200spmv_csr_flat_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz,
-                                            const void* col_ind, const void* values, int32_t base, const void* alpha,
-                                            const void* beta, int scalars_on_device, const void* x, void* y,
-                                            void* workspace);
+                                            const void* row_offsets, const void* col_ind, const void* values,
+                                            int32_t base, const void* alpha, const void* beta, int scalars_on_device,
+                                            const void* x, void* y, void* workspace);
 /* byte offsets of the flat plan's arrays inside its workspace: endmask (uint32 per 32 non-zeros, zero-padded to a
- * multiple of 64 words), chunk_run (int32 per 256 non-zeros + 1), nzrow (int32, rows + 2), control words
+ * multiple of 64 words), chunk_run (int32 per 256 non-zeros, padded to whole groups of 8, + 1), nzrow (int32, rows + 2), control words
  * {non-empty rows, steps without a row end, steps} -- read back by the bit-exact preprocessing tests */
 B200SPMV_EXPORT void   b200spmv_csr_flat_plan_offsets(int64_t rows, int64_t nnz, size_t* endmask, size_t* chunk_run,
                                                       size_t* nzrow, size_t* ctl);

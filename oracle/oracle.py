@@ -77,6 +77,24 @@ def spmv_csr(off, col, val, x, y=None, alpha=1.0, beta=0.0, base=0, threads=1):
     return out
 
 
+def spmm_csr(off, col, val, B, C0=None, alpha=1.0, beta=0.0, base=0, order_b="col", order_c="col", threads=1):
+    """C = alpha*A*B + beta*C0 with B (cols x n) and C0 (rows x n) given as 2-D numpy arrays; `order_*` = memory layout the
+    C loop walks ("col": spmm_csr_example.c:50-66, "row": spmm_csr_op_example.c:195-199).  Returns C as a 2-D array."""
+    off = np.ascontiguousarray(off, np.int32)
+    col = np.ascontiguousarray(col, np.int32)
+    val = np.ascontiguousarray(val)
+    rows, n = off.size - 1, B.shape[1]
+    Bm = np.ascontiguousarray(B, val.dtype) if order_b == "row" else np.asfortranarray(B, val.dtype)
+    out = np.zeros((rows, n), val.dtype) if C0 is None else np.array(C0, val.dtype)
+    Cm = np.ascontiguousarray(out) if order_c == "row" else np.asfortranarray(out)
+    ldb = n if order_b == "row" else B.shape[0]
+    ldc = n if order_c == "row" else rows
+    getattr(lib(), "oracle_spmm_csr_" + _vt(val.dtype))(
+        C.c_int64(rows), C.c_int64(n), _p(off), _p(col), _p(val), C.c_int32(base), C.c_double(alpha), C.c_double(beta), _p(Bm),
+        C.c_int64(ldb), C.c_int(order_b == "row"), _p(Cm), C.c_int64(ldc), C.c_int(order_c == "row"), C.c_int(threads))
+    return np.array(Cm)
+
+
 def spmv_coo(rows, row, col, val, x, y=None, alpha=1.0, beta=0.0, base=0):
     row = np.ascontiguousarray(row, np.int32)
     col = np.ascontiguousarray(col, np.int32)
@@ -234,4 +252,7 @@ TOY = dict(
     sell_val=np.array([1, 4, 2, 0, 3, 0, 5, 8, 6, 9, 7, 0], np.float32),       # spmv_sell_example.c:61-66
     x=np.array([1, 2, 3, 4], np.float32),
     y_result=np.array([19, 8, 51, 52], np.float32),                            # spmv_csr_example.c:54
+    # spmm_csr_example.c:59-66: B 4x3 and the golden C 4x3, both column-major
+    spmm_B=np.arange(1, 13, dtype=np.float32).reshape(3, 4).T.copy(),
+    spmm_C=np.array([19, 8, 51, 52, 43, 24, 123, 120, 67, 40, 195, 188], np.float32).reshape(3, 4).T.copy(),
 )

@@ -82,6 +82,36 @@ DEF_CSR(oracle_spmv_csr_f64, double)
 DEF_CSR(oracle_spmv_csr_f32, float)
 
 /* ------------------------------------------------------------------------- */
+/* CSR x dense (SpMM): C = alpha*A*B + beta*C.  The reference holds no host loop */
+/* for it; this is the CSR row loop above applied per column of B, with the      */
+/* sample's layouts (cuSPARSE/spmm_csr/spmm_csr_example.c:50-66: column-major,   */
+/* ldb = B rows, ldc = A rows; spmm_csr_op_example.c:195-199 uses row-major).    */
+/* Pinned by the sample's golden hC_result (spmm_csr_example.c:64-66).           */
+/* ------------------------------------------------------------------------- */
+#define DEF_SPMM(NAME, T)                                                       \
+EXPORT void NAME(int64_t rows, int64_t n, const int32_t* off, const int32_t* col,\
+                 const T* val, int32_t base, double alpha, double beta,         \
+                 const T* B, int64_t ldb, int b_row_major, T* C, int64_t ldc,   \
+                 int c_row_major, int threads) {                                \
+    _Pragma("omp parallel for schedule(dynamic, 256) num_threads(threads > 0 ? threads : 1)") \
+    for (int64_t i = 0; i < rows; i++) {                                        \
+        for (int64_t j = 0; j < n; j++) {                                       \
+            double sum = 0;                                                     \
+            for (int64_t p = off[i] - base; p < off[i + 1] - base; ++p) {       \
+                int64_t k = col[p] - base;                                      \
+                double b = (double)(b_row_major ? B[k * ldb + j] : B[k + j * ldb]); \
+                sum += alpha * (double)val[p] * b;                              \
+            }                                                                   \
+            T* c = c_row_major ? &C[i * ldc + j] : &C[i + j * ldc];             \
+            if (beta != 0.0) sum += beta * (double)*c;                          \
+            *c = (T)sum;                                                        \
+        }                                                                       \
+    }                                                                           \
+}
+DEF_SPMM(oracle_spmm_csr_f64, double)
+DEF_SPMM(oracle_spmm_csr_f32, float)
+
+/* ------------------------------------------------------------------------- */
 /* COO (spmv_coo_example.c:48-54): any order of entries is accepted; the sum   */
 /* per row is taken in storage order in double, then alpha/beta applied the    */
 /* same way as the CSR loop.                                                   */

@@ -2,7 +2,7 @@
 spmv_csr_flat.cu) on the plan restated in oracle/partition_ref.py::flat_plan.
 
 Pins the ALGORITHM without a GPU: the end-lane mask per step, first-row butterfly + segmented scan, the row lookup through
-chunk_run / nzrow, who fills which empty rows, the deferred first row end of every warp chunk, the per-CTA stitch and the
+chunk_run / nzrow, the empty-row pass, the deferred first row end of every warp chunk, the per-CTA stitch and the
 cross-CTA fix-up -- every row must be written exactly once.  The kernel itself runs under tests/test_parity_gpu.py."""
 import numpy as np
 import pytest
@@ -70,7 +70,6 @@ def emulate(off, col, val, x, y0, alpha, beta):
                     res = np.where(lane == e1, t1, q)
                     is_end = ((m >> lane) & 1).astype(bool)
                     j = run + np.array([bin(m & ((1 << int(l)) - 1)).count("1") for l in lane])
-                    rlo = np.where(is_end, nzrow[np.minimum(j, nruns)], 0)
                     row = np.where(is_end, nzrow[np.minimum(j + 1, nruns + 1)], 0)
                     deferred = -1
                     if frow < 0:
@@ -78,11 +77,6 @@ def emulate(off, col, val, x, y0, alpha, beta):
                     for l in lane[is_end]:
                         if l != deferred:
                             store(int(row[l]), float(res[l]))
-                        for r in range(int(rlo[l]) + 1, int(row[l])):       # empty rows in front of my row
-                            store(r, 0.0)
-                        if j[l] == nruns - 1:                               # the matrix' last non-empty row
-                            for r in range(int(row[l]) + 1, rows):
-                                store(r, 0.0)
                     run += bin(m).count("1")
                     acc = np.where(lane > ek, pk, 0.0)
                 el = n1 - 1 - n0
@@ -112,7 +106,10 @@ def emulate(off, col, val, x, y0, alpha, beta):
         else:
             cta_last[cta] = running
         cta_flags[cta] = int(has)
-    for t in range(nctas - 1):                                   # csr_flat_fixup_kernel
+    for r in range(rows):                                        # csr_flat_fixup_kernel, part 2: the empty rows
+        if off[r] == off[r + 1]:
+            store(r, 0.0)
+    for t in range(nctas - 1):                                   # csr_flat_fixup_kernel, part 1: rows crossing CTA borders
         if (int(mask[(t + 1) * 64 - 1]) >> 31) & 1:
             continue
         has = cta_flags[t] != 0

@@ -128,3 +128,21 @@ def test_empty_and_ragged():
     assert np.array_equal(y, [5, 5, 2 * (2 + 12) + 5, 5, 2 * (3 + 12 + 20) + 5, 5])
     # zero-size
     assert O.spmv_csr(np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0), np.zeros(0)).size == 0
+
+
+def test_spmm_golden_of_the_reference_sample():
+    """cuSPARSE/spmm_csr/spmm_csr_example.c:59-66: hB, hC_result (column-major 4x3), exact `!=` compare at :143-151."""
+    T = O.TOY
+    want = np.array([19, 8, 51, 52, 43, 24, 123, 120, 67, 40, 195, 188], np.float32)
+    for ob in ("col", "row"):
+        for oc in ("col", "row"):
+            C = O.spmm_csr(T["csr_off"], T["csr_col"], T["val"], T["spmm_B"], order_b=ob, order_c=oc)
+            assert np.array_equal(np.asfortranarray(C).T.reshape(-1), want), (ob, oc)
+    # alpha / beta and fp64, against scipy
+    import scipy.sparse as sp
+    off, col, val = O.rmat_csr(500, avg_nnz=6, seed=1, val_seed=2)
+    A = sp.csr_matrix((val, col, off), shape=(500, 500))
+    rng = np.random.default_rng(0)
+    B, C0 = rng.uniform(-1, 1, (500, 7)), rng.uniform(-1, 1, (500, 7))
+    got = O.spmm_csr(off, col, val, B, C0, alpha=-0.5, beta=2.0, order_b="row", order_c="col", threads=2)
+    assert np.allclose(got, -0.5 * (A @ B) + 2.0 * C0, rtol=1e-13, atol=1e-13)

@@ -496,6 +496,91 @@ def test_sell_ragged_rmat(cs, b200):
     assert relerr(got, O.spmv_csr(off, col, val, x, y0, 1.0, 2.0)) < 1e-12
 
 
+# ------------------------------------------------------------------------------------------ Matrix Market input
+@pytest.mark.parametrize("name", ["toy_4x4.mtx", "rmat_300.mtx", "sym_lower_5.mtx"])
+def test_matrix_market_files_through_the_spmv_path(cs, b200, closed, name):
+    """matrices read the way cuDSS/simple_matrix_market/matrix_market_reader.h reads them, then the
+    sample's cusparseCreateCsr / cusparseSpMV sequence; checked against the oracle and the closed library."""
+    from cudalibrarysamples_b200.mtx import read_matrix_market
+    n, m, off, col, val = read_matrix_market(os.path.join(ROOT, "tests", "golden", name))
+    x, y0 = O.uniform(1, m), O.uniform(2, n)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    want = O.spmv_csr(off, col, val, x, y0, 2.0, -1.0)
+    got = run(cs, b200, "csr", n, m, arrays, dev(x), dev(y0), 2.0, -1.0).cpu().numpy()
+    lib = run(cs, closed, "csr", n, m, arrays, dev(x), dev(y0), 2.0, -1.0).cpu().numpy()
+    assert relerr(got, want) < 1e-13 and relerr(got, lib) < 1e-13
+
+
+# ------------------------------------------------------------------------------------------ SpMM (CSR x dense)
+def _dense(buf2d, order, dtype):
+    """2-D numpy matrix -> 1-D device buffer in the given cuSPARSE order with the tight leading dimension"""
+    a = np.ascontiguousarray(buf2d, NP[dtype]) if order == 2 else np.asfortranarray(buf2d, NP[dtype])
+    return dev(a.reshape(-1, order="C" if order == 2 else "F").copy())
+
+
+def _undense(t, shape, order):
+    return t.cpu().numpy().reshape(shape, order="C" if order == 2 else "F")
+
+
+def test_spmm_reference_golden(cs, b200):
+    # spmm_csr_example.c:50-66,143-151: fp32, column-major, exact compare
+    T = O.TOY
+    arrays = dict(off=dev(T["csr_off"]), col=dev(T["csr_col"]), val=dev(T["val"]))
+    before = b200.stats()
+    C = cs.spmm(b200, 4, 4, arrays, _dense(T["spmm_B"], 1, torch.float32), torch.zeros(12, device="cuda"), 1.0, 0.0)
+    assert np.array_equal(C.cpu().numpy(), np.array([19, 8, 51, 52, 43, 24, 123, 120, 67, 40, 195, 188], np.float32))
+    after = b200.stats()
+    assert after["native"] == before["native"] + 1 and after["forwarded"] == before["forwarded"]
+
+
+def test_spmm_sample_passes_through_the_shim():
+    exe = os.path.join(ROOT, "oracle", "_ref", "spmm_csr_example.b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=clean_env(B200SPMV_LOG="1"))
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "spmm_csr_example test PASSED" in p.stdout
+    assert "[b200spmv] SpMM spmm_csr_kernel" in p.stderr and "forwarded" not in p.stderr
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("order_b,order_c", [(1, 1), (2, 2), (2, 1), (1, 2)])
+@pytest.mark.parametrize("n", [1, 64, 70])
+def test_spmm_vs_oracle_and_cusparse(cs, b200, closed, dtype, order_b, order_c, n):
+    rows = 3000
+    off, col, val, _, _ = rmat_case(rows, 12, dtype, 131)
+    rng = np.random.default_rng(n)
+    B = rng.uniform(-1, 1, (rows, n)).astype(NP[dtype])
+    C0 = rng.uniform(-1, 1, (rows, n)).astype(NP[dtype])
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    ob, oc = ("row" if order_b == 2 else "col"), ("row" if order_c == 2 else "col")
+    for alpha, beta in [(1.0, 0.0), (-0.5, 2.0)]:
+        want = O.spmm_csr(off, col, val, B, C0, alpha, beta, order_b=ob, order_c=oc, threads=4)
+        got = _undense(cs.spmm(b200, rows, rows, arrays, _dense(B, order_b, dtype), _dense(C0, order_c, dtype), alpha, beta,
+                               order_b, order_c), (rows, n), order_c)
+        assert relerr(got, want) < TOL[dtype], (order_b, order_c, n, alpha, beta)
+        if order_b == order_c:      # the closed library wants B and C in the same order
+            lib = _undense(cs.spmm(closed, rows, rows, arrays, _dense(B, order_b, dtype), _dense(C0, order_c, dtype), alpha, beta,
+                                   order_b, order_c), (rows, n), order_c)
+            assert relerr(got, lib) < TOL[dtype]
+
+
+def test_spmm_edge_rows_and_base_one(cs, b200):
+    lens = np.concatenate([[0, 0, 700, 1, 0, 33, 32, 31], np.zeros(40, int), [5, 64, 0]])
+    off, col, val = lens_to_csr(lens, 900, 5)
+    rng = np.random.default_rng(1)
+    B, C0 = rng.uniform(-1, 1, (900, 9)), rng.uniform(-1, 1, (lens.size, 9))
+    want = O.spmm_csr(off, col, val, B, C0, 1.5, -1.0, order_b="row", order_c="row")
+    arrays = dict(off=dev(off + 1), col=dev(col + 1), val=dev(val))
+    got = _undense(cs.spmm(b200, lens.size, 900, arrays, _dense(B, 2, torch.float64), _dense(C0, 2, torch.float64), 1.5, -1.0, 2, 2,
+                           base=1), (lens.size, 9), 2)
+    assert relerr(got, want) < 1e-12
+    # beta == 0 must not read C (NaN in, finite out)
+    nanC = torch.full((lens.size * 9,), float("nan"), dtype=torch.float64, device="cuda")
+    got = _undense(cs.spmm(b200, lens.size, 900, arrays, _dense(B, 2, torch.float64), nanC, 1.0, 0.0, 2, 2, base=1), (lens.size, 9), 2)
+    assert relerr(got, O.spmm_csr(off, col, val, B, None, 1.0, 0.0, order_b="row", order_c="row")) < 1e-12
+
+
 # ------------------------------------------------------------------ bit-exact integer work on the device
 def read_plan(buffer, num_tiles):
     from cudalibrarysamples_b200 import lib
