@@ -58,7 +58,7 @@ def conjugate_gradient(sh: ShardedCsr, b_shard: torch.Tensor, iters: int, x0_sha
 
 
 class CgSolver:
-    """conjugate_gradient() packaged for repeated timed runs (bench.py's cg_config4 leg, scripts/cg_bench.py)."""
+    """conjugate_gradient() packaged for repeated timed runs (bench.py's cg_config4 leg, scripts/cg_bench.py): torch ops."""
 
     def __init__(self, sh: ShardedCsr, b_shard: torch.Tensor):
         self.sh, self.b = sh, b_shard
@@ -72,5 +72,111 @@ class CgSolver:
                 "single-pass torch ops (addcmul), dots all-reduced over ranks, no host synchronisation inside the loop")
 
 
-def make_cg_solver(sh: ShardedCsr, b_shard: torch.Tensor) -> CgSolver:
-    return CgSolver(sh, b_shard)
+class FusedCgSolver:
+    """The same iteration on the fused sm_100a BLAS-1 kernels of csrc/cg_fused.cu (b200cg_dot / _update_xr / _update_p): per
+    iteration 1 SpMV + 3 kernels, every scalar in device memory, partial dots all-reduced over ranks; on one GPU two
+    iterations are captured in a CUDA graph and replayed (graph_capture_example.c:118-135 pattern)."""
+
+    def __init__(self, sh: ShardedCsr, b_shard: torch.Tensor, use_graph: bool | None = None):
+        import ctypes as C
+        import os
+        from . import lib as _lib
+        self.C, self.L = C, _lib.shim()
+        self.L.b200cg_workspace_bytes.restype = C.c_size_t
+        self.sh, self.b = sh, b_shard
+        self.n = int(b_shard.numel())
+        dev = b_shard.device
+        self.ws = torch.zeros(int(self.L.b200cg_workspace_bytes()), dtype=torch.uint8, device=dev)
+        self.scal = torch.zeros(8, dtype=torch.float64, device=dev)        # [0], [1]: delta of even / odd iterations, [2]: t.p
+        self.use_graph = (sh.world == 1 and os.environ.get("B200CG_GRAPH", "1") != "0") if use_graph is None else use_graph
+        self.graph_error = None
+
+    def _stream(self):
+        return self.C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed with code {rc}")
+
+    def _p(self, t):
+        return self.C.c_void_p(t.data_ptr())
+
+    def _dot(self, a, b, out):
+        self._check(self.L.b200cg_dot(self._stream(), self.C.c_int64(self.n), self._p(a), self._p(b), self._p(out), self._p(self.ws)), "b200cg_dot")
+        if self.sh.world > 1:
+            dist.all_reduce(out, group=self.sh.group)
+
+    def _iteration(self, x, r, p, t, cur):
+        """one CG iteration; delta_k lives in scal[cur], delta_{k+1} goes to scal[1 - cur]"""
+        C, s = self.C, self.scal
+        self.sh.spmv(p, t, alpha=1.0, beta=0.0)                              # T = A * P      (cg_example.c:220-224)
+        self._dot(t, p, s[2:3])                                              # denom = T . P  (:227)
+        nxt = 1 - cur
+        self._check(self.L.b200cg_update_xr(self._stream(), C.c_int64(self.n), self._p(x), self._p(r), self._p(p), self._p(t),
+                                            self._p(s[cur:cur + 1]), self._p(s[2:3]), self._p(s[nxt:nxt + 1]), self._p(self.ws)),
+                    "b200cg_update_xr")                                      # X += aP, R -= aT, delta' = R.R (:232-247)
+        if self.sh.world > 1:
+            dist.all_reduce(s[nxt:nxt + 1], group=self.sh.group)
+        self._check(self.L.b200cg_update_p(self._stream(), C.c_int64(self.n), self._p(p), self._p(r), self._p(s[nxt:nxt + 1]),
+                                           self._p(s[cur:cur + 1])), "b200cg_update_p")   # P = R + (delta'/delta) P (:280-286)
+
+    def run(self, iters: int):
+        x = torch.zeros_like(self.b)
+        r = self.b.clone()
+        p = r.clone()
+        t = torch.zeros_like(self.b)
+        self._dot(r, r, self.scal[0:1])
+        first = self.scal[0:1].clone()
+        done = 0
+        if self.use_graph and iters >= 4 and self.graph_error is None:
+            try:
+                done = self._run_graphed(x, r, p, t, iters)
+            except Exception as e:                   # capture refused (driver / library version): plain launches instead
+                self.graph_error = repr(e)
+                torch.cuda.synchronize()
+                x.zero_(); r.copy_(self.b); p.copy_(self.b)
+                self._dot(r, r, self.scal[0:1])
+                done = 0
+        for k in range(done, iters):
+            self._iteration(x, r, p, t, k & 1)
+        last = self.scal[iters & 1:(iters & 1) + 1]
+        norms = torch.cat([first, last]).sqrt()
+        return x, [float(v) for v in norms.tolist()]
+
+    def _run_graphed(self, x, r, p, t, iters):
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(main)
+        ops = [op for op in (getattr(self.sh, "local_op", None), getattr(self.sh, "own_op", None)) if op is not None and hasattr(op, "handle")]
+        with torch.cuda.stream(side):
+            for op in ops:
+                op.api.cusparseSetStream(op.handle, side.cuda_stream)
+            self._iteration(x, r, p, t, 0)            # two eager iterations: warm-up of every kernel on this stream
+            self._iteration(x, r, p, t, 1)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._iteration(x, r, p, t, 0)
+                self._iteration(x, r, p, t, 1)
+            done = 4                                  # the capture pass does not execute: 2 eager + first replay below = 4
+            g.replay()
+            while done + 2 <= iters:
+                g.replay()
+                done += 2
+        main.wait_stream(side)
+        for op in ops:
+            op.api.cusparseSetStream(op.handle, main.cuda_stream)
+        self._graph = g
+        return done
+
+    def describe(self) -> str:
+        how = "two iterations captured in a CUDA graph and replayed" if self.use_graph and self.graph_error is None else "plain stream launches"
+        return ("CG (cg_example.c:215-287 without the IC(0) preconditioner): SpMV through the C ABI + fused sm_100a BLAS-1 kernels "
+                "(b200cg_dot, b200cg_update_xr = 2 axpy + nrm2 in one pass, b200cg_update_p), all scalars on the device, "
+                + how + (f" (graph capture failed: {self.graph_error})" if self.graph_error else ""))
+
+
+def make_cg_solver(sh: ShardedCsr, b_shard: torch.Tensor, fused: bool | None = None):
+    """The fused driver on CUDA (the product), the torch-op driver on CPU (gloo tests with the oracle as local kernel)."""
+    if fused is None:
+        fused = b_shard.is_cuda
+    return FusedCgSolver(sh, b_shard) if fused else CgSolver(sh, b_shard)

@@ -28,7 +28,7 @@
 namespace b200 {
 
 #ifndef B200_FLAT_MIN_CTAS
-#define B200_FLAT_MIN_CTAS 4
+#define B200_FLAT_MIN_CTAS 10     // x 128 threads, 48 registers (sweep r2e: 84.1 us on R-MAT 1M; 8 x 256 threads at 56 registers: 90.4 us)
 #endif
 #ifndef B200_FLAT_BATCH
 #define B200_FLAT_BATCH 4
@@ -36,7 +36,7 @@ namespace b200 {
 constexpr int FLAT_STEPS = 8;                      // 32-element steps per warp chunk
 constexpr int FLAT_CHUNK = 32 * FLAT_STEPS;        // 256 non-zeros per warp
 #ifndef B200_FLAT_WARPS
-#define B200_FLAT_WARPS 8
+#define B200_FLAT_WARPS 4
 #endif
 constexpr int FLAT_WARPS = B200_FLAT_WARPS;         // warp chunks stitched per CTA (a divisor of 8)
 constexpr int FLAT_BLOCK = 32 * FLAT_WARPS;

@@ -83,6 +83,20 @@ B200SPMV_EXPORT int b200spmm_csr(void* stream, int dtype, int64_t rows, int64_t 
                                  const void* alpha, const void* beta, int scalars_on_device, const void* B, int64_t ldb,
                                  int b_row_major, void* C, int64_t ldc, int c_row_major);
 
+/* The BLAS-1 part of a CG iteration, fused, all scalars in DEVICE memory (no host synchronisation, CUDA-graph capturable).
+ * Replaces the cublasDdot / cublasDaxpy / cublasDnrm2 / cublasDscal calls between two cusparseSpMV calls of gpu_CG
+ * (cuSPARSE/cg/cg_example.c:226-286).  fp64; vectors 16-byte aligned; `workspace` = b200cg_workspace_bytes() bytes, zeroed
+ * once by the caller.
+ *   b200cg_dot        *out = a . b
+ *   b200cg_update_xr  alpha = *delta / *denom;  x += alpha p;  r -= alpha t;  *delta_new = r . r   (one pass)
+ *   b200cg_update_p   beta = *delta_new / *delta;  p = r + beta p */
+B200SPMV_EXPORT size_t b200cg_workspace_bytes(void);
+B200SPMV_EXPORT int    b200cg_dot(void* stream, int64_t n, const double* a, const double* b, double* out, void* workspace);
+B200SPMV_EXPORT int    b200cg_update_xr(void* stream, int64_t n, double* x, double* r, const double* p, const double* t,
+                                        const double* delta, const double* denom, double* delta_new, void* workspace);
+B200SPMV_EXPORT int    b200cg_update_p(void* stream, int64_t n, double* p, const double* r, const double* delta_new,
+                                       const double* delta);
+
 /* COO (row-sorted or not).  Replaces cusparseSpMV for cusparseCreateCoo descriptors
  * (cuSPARSE/spmv_coo/spmv_coo_example.c:86-104). */
 B200SPMV_EXPORT size_t b200spmv_coo_workspace_bytes(int64_t rows, int64_t nnz);

@@ -10,14 +10,20 @@ import pytest
 from oracle import oracle as O
 from oracle.partition_ref import flat_plan
 
-STEPS, CHUNK, WARPS, CTA = 8, 256, 8, 2048
+STEPS, CHUNK = 8, 256
+WARPS = 4                      # B200_FLAT_WARPS: warp chunks stitched per CTA (the plan itself does not depend on it)
+CTA = CHUNK * WARPS
+CTA_WORDS = CTA // 32
 
 
 def axpby(alpha, s, beta, yv):
     return alpha * s if beta == 0 else alpha * s + beta * yv
 
 
-def emulate(off, col, val, x, y0, alpha, beta):
+def emulate(off, col, val, x, y0, alpha, beta, warps=None):
+    global WARPS, CTA, CTA_WORDS
+    if warps is not None:
+        WARPS, CTA, CTA_WORDS = warps, CHUNK * warps, CHUNK * warps // 32
     off = off.astype(np.int64)
     rows, nnz = off.size - 1, int(off[-1])
     y = y0.astype(np.float64).copy()
@@ -89,7 +95,7 @@ def emulate(off, col, val, x, y0, alpha, beta):
             else:
                 sFirst[warp], sLast[warp] = last, 0.0
             sFrow[warp] = frow
-        starts_row = cta == 0 or (int(mask[cta * 64 - 1]) >> 31) & 1
+        starts_row = cta == 0 or (int(mask[cta * CTA_WORDS - 1]) >> 31) & 1
         running, has = 0.0, False
         for w in range(WARPS):
             if sFrow[w] >= 0:
@@ -110,10 +116,10 @@ def emulate(off, col, val, x, y0, alpha, beta):
         if off[r] == off[r + 1]:
             store(r, 0.0)
     for t in range(nctas - 1):                                   # csr_flat_fixup_kernel, part 1: rows crossing CTA borders
-        if (int(mask[(t + 1) * 64 - 1]) >> 31) & 1:
+        if (int(mask[(t + 1) * CTA_WORDS - 1]) >> 31) & 1:
             continue
         has = cta_flags[t] != 0
-        starts_row = t == 0 or (int(mask[t * 64 - 1]) >> 31) & 1
+        starts_row = t == 0 or (int(mask[t * CTA_WORDS - 1]) >> 31) & 1
         if not has and not starts_row:
             continue
         s = cta_last[t] if has else cta_first[t]
@@ -185,11 +191,12 @@ def test_flat_kernel_random_structures(seed):
     assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
 
 
-def test_flat_kernel_on_rmat():
+@pytest.mark.parametrize("warps", [8, 4, 2])
+def test_flat_kernel_on_rmat(warps):
     off, col, val = O.rmat_csr(40000, avg_nnz=16, seed=3, val_seed=4)
     x, y0 = O.uniform(5, 40000), O.uniform(6, 40000)
     want = O.spmv_csr(off, col, val, x, y0, 1.5, -0.25)
-    got, written = emulate(off, col, val, x, y0, 1.5, -0.25)
+    got, written = emulate(off, col, val, x, y0, 1.5, -0.25, warps=warps)
     assert np.all(written == 1)
     assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
 

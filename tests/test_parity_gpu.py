@@ -496,6 +496,47 @@ def test_sell_ragged_rmat(cs, b200):
     assert relerr(got, O.spmv_csr(off, col, val, x, y0, 1.0, 2.0)) < 1e-12
 
 
+# ------------------------------------------------------------------------------------------ fused CG step (8(f)-2)
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_cg_matches_the_sample_loop(cs, b200, graph):
+    """The fused device-scalar CG driver (csrc/cg_fused.cu) against a plain numpy restatement of cg_example.c:215-287
+    (no preconditioner) on the sample's own matrix family; with and without CUDA-graph replay."""
+    from cudalibrarysamples_b200.cg import CgSolver, FusedCgSolver
+    from cudalibrarysamples_b200.sharded import ShardedCsr
+    grid = 96
+    off, col, val = O.gen_stencil5(grid)
+    n = grid * grid
+    b = O.spmv_csr(off, col, val, np.ones(n), alpha=0.75)            # cg_example.c:405-418
+    # reference loop on the CPU with the oracle SpMV
+    x = np.zeros(n); r = b.copy(); p = r.copy(); delta = r @ r
+    iters = 25
+    for _ in range(iters):
+        t = O.spmv_csr(off, col, val, p)
+        alpha = delta / (t @ p)
+        x += alpha * p; r -= alpha * t
+        dn = r @ r
+        p = r + (dn / delta) * p
+        delta = dn
+
+    def make_local(rr, cc, arrays):
+        return cs.SpMVOperator(b200, "csr", rr, cc, arrays, preprocess=True)
+    sh = ShardedCsr(dev(off), dev(col), dev(val), 0, 1, make_local, balance="rows")
+    solver = FusedCgSolver(sh, dev(b), use_graph=graph)
+    xs, norms = solver.run(iters)
+    torch.cuda.synchronize()
+    assert solver.graph_error is None, solver.graph_error
+    assert abs(norms[0] - np.sqrt(b @ b)) <= 1e-12 * np.sqrt(b @ b)
+    assert abs(norms[-1] - np.sqrt(delta)) <= 1e-6 * np.sqrt(delta)          # 25 iterations of rounding differences
+    assert relerr(xs.cpu().numpy(), x) < 1e-9
+    # a second run on the same solver (bench: warm-up run, then the timed run) gives the same answer
+    xs2, norms2 = solver.run(iters)
+    assert torch.equal(xs, xs2) and norms2 == norms
+    # and the torch-op driver agrees
+    xt, nt = CgSolver(sh, dev(b)).run(iters)
+    assert relerr(xt.cpu().numpy(), x) < 1e-9
+    sh.close()
+
+
 # ------------------------------------------------------------------------------------------ Matrix Market input
 @pytest.mark.parametrize("name", ["toy_4x4.mtx", "rmat_300.mtx", "sym_lower_5.mtx"])
 def test_matrix_market_files_through_the_spmv_path(cs, b200, closed, name):
