@@ -33,8 +33,20 @@ namespace b200 {
 #ifndef B200_FLAT_BATCH
 #define B200_FLAT_BATCH 4
 #endif
-constexpr int FLAT_STEPS = 8;                      // 32-element steps per warp chunk
-constexpr int FLAT_CHUNK = 32 * FLAT_STEPS;        // 256 non-zeros per warp
+#ifndef B200_FLAT_STEPS
+#define B200_FLAT_STEPS 8
+#endif
+#ifndef B200_FLAT_KBLOOP     // 1: the loop over the batches of a chunk is a run-time loop (code size independent of FLAT_STEPS)
+#define B200_FLAT_KBLOOP (B200_FLAT_STEPS > 8)
+#endif
+#ifndef B200_FLAT_NZPRE      // 1: the chunk's first 32 nzrow entries are loaded with the stream and looked up by shuffle
+#define B200_FLAT_NZPRE 1
+#endif
+constexpr int PLAN_STEPS = 8;                      // the plan's granularity: chunk_run has one entry per 8 steps = 256 non-zeros
+constexpr int PLAN_CHUNK = 32 * PLAN_STEPS;
+constexpr int FLAT_STEPS = B200_FLAT_STEPS;        // 32-element steps per warp chunk (8, 16 or 32)
+constexpr int FLAT_CHUNK = 32 * FLAT_STEPS;        // non-zeros per warp
+static_assert(FLAT_STEPS % PLAN_STEPS == 0 && FLAT_STEPS <= 32, "a warp chunk is 1, 2 or 4 plan chunks");
 #ifndef B200_FLAT_WARPS
 #define B200_FLAT_WARPS 4
 #endif
@@ -43,7 +55,7 @@ constexpr int FLAT_BLOCK = 32 * FLAT_WARPS;
 constexpr int FLAT_CTA_NNZ = FLAT_CHUNK * FLAT_WARPS;   // 2048 non-zeros per CTA
 constexpr int FLAT_CTA_WORDS = FLAT_CTA_NNZ / 32;
 constexpr int FLAT_PAD_NNZ = 2048;                 // the plan arrays are padded to this many non-zeros (independent of FLAT_WARPS)
-static_assert(FLAT_PAD_NNZ % FLAT_CTA_NNZ == 0, "FLAT_WARPS must divide 8");
+static_assert(FLAT_PAD_NNZ % FLAT_CTA_NNZ == 0, "FLAT_WARPS x FLAT_STEPS must divide 64");
 constexpr int FLAT_BATCH = B200_FLAT_BATCH;
 constexpr int SCAN_ITEMS = 2048;                   // items per block of the preprocessing scans
 static_assert(FLAT_STEPS % FLAT_BATCH == 0, "steps per chunk must be a multiple of the batch");
@@ -61,16 +73,16 @@ struct FlatPlan {
 
 static inline size_t flat_align(size_t v) { return (v + 255) / 256 * 256; }
 static inline int64_t flat_num_ctas(int64_t nnz) { return (nnz + FLAT_CTA_NNZ - 1) / FLAT_CTA_NNZ; }
-static inline int64_t flat_num_chunks_padded(int64_t nnz) { return (nnz + FLAT_PAD_NNZ - 1) / FLAT_PAD_NNZ * (FLAT_PAD_NNZ / FLAT_CHUNK); }
+static inline int64_t flat_num_chunks_padded(int64_t nnz) { return (nnz + FLAT_PAD_NNZ - 1) / FLAT_PAD_NNZ * (FLAT_PAD_NNZ / PLAN_CHUNK); }
 
 static size_t flat_layout(int64_t rows, int64_t nnz, void* ws, FlatPlan* p) {
     const size_t nchunks = (size_t)flat_num_chunks_padded(nnz);
     const size_t nctas = nchunks;                                  // upper bound for every FLAT_WARPS (one CTA per chunk)
     const size_t nscan = (size_t)((rows > (int64_t)nchunks ? rows : (int64_t)nchunks) / SCAN_ITEMS + 2);
     size_t o = 0;
-    const size_t o_mask = o;  o = flat_align(o + nchunks * FLAT_STEPS * sizeof(unsigned));
+    const size_t o_mask = o;  o = flat_align(o + nchunks * PLAN_STEPS * sizeof(unsigned));
     const size_t o_crun = o;  o = flat_align(o + (nchunks + 1) * sizeof(int));
-    const size_t o_nzr  = o;  o = flat_align(o + ((size_t)rows + 2) * sizeof(int));
+    const size_t o_nzr  = o;  o = flat_align(o + ((size_t)rows + 2 + 32) * sizeof(int));   // + 32: the kernel's look-ahead window
     const size_t o_cf   = o;  o = flat_align(o + nctas * sizeof(double));
     const size_t o_cl   = o;  o = flat_align(o + nctas * sizeof(double));
     const size_t o_fl   = o;  o = flat_align(o + nctas * sizeof(int));
@@ -105,7 +117,7 @@ struct ChunkEnds {
     __device__ __forceinline__ int operator()(int64_t c) const {
         int n = 0;
 #pragma unroll
-        for (int k = 0; k < FLAT_STEPS; k++) n += __popc(endmask[c * FLAT_STEPS + k]);
+        for (int k = 0; k < PLAN_STEPS; k++) n += __popc(endmask[c * PLAN_STEPS + k]);
         return n;
     }
 };
@@ -265,7 +277,11 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
     if (active) {
         const int n0 = (int)c0, n1 = min(n0 + FLAT_CHUNK, a.nnz);
         const unsigned mreg = lane < FLAT_STEPS ? __ldg(a.plan.endmask + c * FLAT_STEPS + lane) : 0u;
-        int run = __ldg(a.plan.chunk_run + c);             // rows that ended before this chunk
+        int run = __ldg(a.plan.chunk_run + c * (FLAT_STEPS / PLAN_STEPS));   // rows that ended before this chunk
+#if B200_FLAT_NZPRE
+        const int run0 = run;
+        const int nzw = __ldg(a.plan.nzrow + run0 + 1 + lane);              // rows of the chunk's first 32 row ends
+#endif
         const int* colp = a.col + n0;
         const T*   valp = a.val + n0;
         const T*   xp = a.x - a.base;
@@ -284,7 +300,11 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
         // Unrolled over the 8 steps (static register indexing, no loop control), but the scan inside a flush is a run-time
         // loop: with everything unrolled the kernel was 106 KB of SASS and stalled on instruction fetch (160 us); with
         // run-time step loops it was 20 KB but executed 61 M instructions, 45 % of them select chains / loop control (109 us).
+#if B200_FLAT_KBLOOP
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int kb = 0; kb < FLAT_STEPS; kb += FLAT_BATCH) {
             if (n0 + kb * 32 >= n1) break;                 // warp-uniform: the matrix' last chunk may be short
             T p[FLAT_BATCH];
@@ -300,7 +320,15 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
                 // my row (if I end one): issued first, the look-up's latency hides behind the shuffles below
                 const bool is_end = (m >> lane) & 1u;
                 int row = 0;
+#if B200_FLAT_NZPRE
+                {
+                    const int j = run - run0 + __popc(m & ((1u << lane) - 1u));     // my row end is the chunk's j-th
+                    row = __shfl_sync(0xffffffffu, nzw, j & 31);
+                    if (is_end && j >= 32) row = __ldg(a.plan.nzrow + run0 + j + 1); // more than 32 rows end in this chunk
+                }
+#else
                 if (is_end) row = __ldg(a.plan.nzrow + run + __popc(m & ((1u << lane) - 1u)) + 1);   // (run + k)-th non-empty row
+#endif
                 const T t1 = flat_allsum(acc + (lane <= e1 ? pk : T(0)));
                 T q = (lane > e1 && lane <= ek) ? pk : T(0);
                 if (m & (m - 1u)) {                        // more rows end: segmented inclusive scan
@@ -383,7 +411,7 @@ __global__ void __launch_bounds__(256) csr_flat_fixup_kernel(const FlatArgs<T> a
     long long u = t + 1;
     while (__ldcg(a.plan.cta_flags + u) == 0) { sum += __ldcg(a.plan.cta_first + u); u++; }
     sum += __ldcg(a.plan.cta_first + u);
-    const int row = __ldg(a.plan.nzrow + __ldg(a.plan.chunk_run + u * FLAT_WARPS) + 1);
+    const int row = __ldg(a.plan.nzrow + __ldg(a.plan.chunk_run + u * (FLAT_CTA_NNZ / PLAN_CHUNK)) + 1);
     flat_store_y(a.y + row, alpha, (T)sum, beta);
 }
 
@@ -437,7 +465,7 @@ int b200spmv_csr_flat_analyze(void* stream_, int64_t rows, int64_t nnz, const vo
     const size_t total = flat_layout(rows, nnz, workspace, &p);
     (void)total;
     const int64_t nchunks = flat_num_chunks_padded(nnz), nwords = (nnz + 31) / 32;
-    cudaError_t e = cudaMemsetAsync(p.endmask, 0, (size_t)nchunks * FLAT_STEPS * sizeof(unsigned), stream);
+    cudaError_t e = cudaMemsetAsync(p.endmask, 0, (size_t)nchunks * PLAN_STEPS * sizeof(unsigned), stream);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(p.ctl, 0, 64, stream);
     if (e != cudaSuccess) return (int)e;

@@ -191,6 +191,8 @@ class ShardedCsr:
         how = {"p2p": "x shards in symmetric memory; one device-side barrier, then copy-engine peer copies over NVLink on side streams "
                       "(double-buffered shards)",
                "allgather": "one NCCL all_gather_into_tensor on a side stream"}[self.exchange]
+        if getattr(self, "_graphs", None):
+            how += "; the whole step replayed as a CUDA graph"
         if self.panels:
             how += (f"; overlapped with the own-column panel of the local product ({self.own_nnz} of {self.nnz} local non-zeros), "
                     "the remote-column panel follows with beta = 1")
@@ -285,9 +287,14 @@ class ShardedCsr:
         self.remote_op(self.x_full, y_shard, alpha, 1.0)
         return y_shard
 
-    def make_step(self, x_shard: torch.Tensor, y_shard: torch.Tensor, local_call=None):
+    def make_step(self, x_shard: torch.Tensor, y_shard: torch.Tensor, local_call=None, graph: bool | None = None):
         """A zero-argument callable for timing loops: one full step y = A x with fixed buffers and alpha = 1, beta = 0;
-        uses the operators' prebuilt calls when they offer them (ctypes arguments built once)."""
+        uses the operators' prebuilt calls when they offer them (ctypes arguments built once).
+
+        graph (default: on CUDA with panels): the step -- shard copies, device-side barrier, peer copies / all-gather on
+        the side streams, both panel kernels -- is captured ONCE per shard-buffer parity into a CUDA graph and replayed:
+        issued from Python the ~15 launches of a step cost more host time (~190 us measured at N = 2) than the step
+        takes on the GPUs.  If the capture is refused the eager step is returned and `self.graph_error` says why."""
         if not self.panels:
             call = local_call
             if call is None:
@@ -307,7 +314,55 @@ class ShardedCsr:
             own_call()
             wait()
             remote_call()
-        return step
+        if graph is None:
+            graph = x_shard.is_cuda and os.environ.get("B200SPMV_STEP_GRAPH", "1") != "0"
+        if not graph:
+            return step
+        try:
+            return self._graphed_step(step)
+        except Exception as e:   # pragma: no cover (GPU boxes only)
+            self.graph_error = repr(e)
+            torch.cuda.synchronize()
+            return step
+
+    def _graphed_step(self, step):
+        """Two graphs, one per parity of the double-buffered x shard (the p2p exchange alternates buffers so that one
+        barrier per step suffices); replayed alternately in the order the eager steps would run."""
+        main = torch.cuda.current_stream()
+        cap = torch.cuda.Stream()
+        ops = [op for op in (self.own_op, self.remote_op) if hasattr(op, "handle")]
+        for _ in range(2):                      # warm-up: both parities, eagerly, on the stream the graphs are captured on
+            step()
+        torch.cuda.synchronize()
+        graphs = []
+        nparity = 2 if self.exchange == "p2p" else 1
+        cap.wait_stream(main)
+        try:
+            with torch.cuda.stream(cap):
+                for op in ops:
+                    op.api.cusparseSetStream(op.handle, cap.cuda_stream)
+                for _ in range(2):
+                    step()
+                cap.synchronize()
+                for i in range(nparity):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=cap):
+                        step()
+                    graphs.append(g)
+        finally:
+            for op in ops:                      # the operators go back to the caller's stream whatever happened
+                op.api.cusparseSetStream(op.handle, main.cuda_stream)
+        main.wait_stream(cap)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self._graphs, self._gi = graphs, 0
+        self.graph_error = None
+
+        def replay():
+            self._graphs[self._gi].replay()
+            self._gi = (self._gi + 1) % len(self._graphs)
+        return replay
 
     def close(self):
         for name in ("own_op", "remote_op", "local_op"):

@@ -95,17 +95,19 @@ if os.environ.get("SWEEP_SET") == "seg":
     VARIANTS["seg_t512_b128_occ12_k2_st0"] = dict(SEG=(12, 2, 0), TILE=512, LONG=128, BLOCK=128)
     VARIANTS["seg_t3072_b384_occ4_k4_st0"] = dict(SEG=(4, 4, 0), TILE=3072, LONG=512, BLOCK=384)
 if os.environ.get("SWEEP_SET") == "flat":
-    # csr_flat_kernel: resident CTAs (register cap), batch depth, warps stitched per CTA
-    VARIANTS = {f"flat_occ{o}_k{k}_w{w}": dict(FLAT=(o, k, w)) for (o, k, w) in
-                [(4, 4, 8), (5, 4, 8), (6, 4, 8), (4, 2, 8), (5, 2, 8), (6, 2, 8), (8, 2, 8), (4, 8, 8), (5, 8, 8),
-                 (10, 2, 4), (12, 2, 4), (16, 2, 4), (10, 4, 4), (12, 4, 4), (20, 2, 2), (24, 4, 2)]}
+    # csr_flat_kernel: (resident CTAs, batch, warps per CTA, steps per warp chunk, nzrow prefetch)
+    VARIANTS = {f"flat_occ{o}_k{k}_w{w}_s{st}_nz{nz}": dict(FLAT=(o, k, w, st, nz)) for (o, k, w, st, nz) in
+                [(10, 4, 4, 8, 0), (10, 4, 4, 8, 1), (12, 4, 4, 8, 1), (8, 4, 4, 8, 1), (10, 2, 4, 8, 1),
+                 (10, 4, 4, 16, 1), (12, 4, 4, 16, 1), (8, 4, 4, 16, 1), (20, 4, 2, 16, 1), (10, 4, 2, 32, 1), (20, 4, 2, 32, 1),
+                 (5, 4, 8, 8, 1), (20, 4, 2, 8, 1), (40, 4, 1, 16, 1), (40, 4, 1, 8, 1)]}
 if os.environ.get("SWEEP_SET") == "ablate":
     VARIANTS = dict(ABL, t2048_b256_k4_occ6=VARIANTS["t2048_b256_k4_occ6"])
 
 
 def flags(v):
     if "FLAT" in v:
-        return [f"-DB200_FLAT_MIN_CTAS={v['FLAT'][0]}", f"-DB200_FLAT_BATCH={v['FLAT'][1]}", f"-DB200_FLAT_WARPS={v['FLAT'][2]}"]
+        o, k, w, st, nz = v["FLAT"]
+        return [f"-DB200_FLAT_MIN_CTAS={o}", f"-DB200_FLAT_BATCH={k}", f"-DB200_FLAT_WARPS={w}", f"-DB200_FLAT_STEPS={st}", f"-DB200_FLAT_NZPRE={nz}"]
     if "SEG" in v:
         o, k, staged = v["SEG"]
         base = dict(TILE=v.get("TILE", 2048), LONG=v.get("LONG", 512), BLOCK=v.get("BLOCK", 256), BATCH=4, MIN=5)
