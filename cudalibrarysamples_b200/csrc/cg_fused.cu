@@ -18,7 +18,7 @@
 namespace b200cg {
 
 constexpr int BLOCK = 256;
-constexpr int MAX_CTAS = 148 * 8;
+constexpr int MAX_CTAS = 148 * 16;   // 256 threads x 16 CTAs/SM candidates: plenty of loads in flight for a pure stream
 
 // workspace: [0 .. MAX_CTAS) partial sums, then one arrival counter (as a double slot)
 __device__ __forceinline__ double block_sum(double v, double* sred) {

@@ -20,4 +20,6 @@ PY
 }
 run p2p "--exchange auto"
 run allgather "--exchange allgather --no-extra"
-B200SPMV_NO_P2P=1 run allgather_nopanel_check "--exchange allgather --no-extra"
+if [ "$N" -le 2 ]; then
+B200SPMV_STEP_GRAPH=0 run p2p_nograph "--exchange auto --no-extra"
+fi
