@@ -16,7 +16,7 @@ and a step is:  start the exchange  ||  y = alpha*A_own*x_own + beta*y   ->   wa
 Exchange mechanisms (chosen at set-up, structure-only, like the kernels' plans):
 
     "p2p"        x shards live in symmetric memory (torch.distributed._symmetric_memory: CUDA IPC / fabric handles mapped
-                 into every rank); one device-side barrier, then every rank PULLS the other shards with copy-engine
+                 into every rank); one device-side barrier (csrc/peer_sync.cu: flags in peer memory, epoch on the device), then every rank PULLS the other shards with copy-engine
                  peer copies over NVLink (no SMs, no NCCL kernels) on side streams, starting with a different peer on every
                  rank so no source is read by two ranks at once.  Double-buffered shards: one barrier per step suffices.
     "allgather"  one NCCL all_gather_into_tensor on a side stream (fallback when symmetric memory is unavailable)
@@ -167,6 +167,18 @@ class ShardedCsr:
             self.peer = [[h.get_buffer(r, (self.x_block,), self.val.dtype) for r in range(self.world)] for h in self.hdl]
             for t in self.sym:
                 t.zero_()
+            # flags of the device-side barrier (csrc/peer_sync.cu): one 8-byte slot per rank in every rank's buffer
+            import ctypes as C
+            from . import lib as _lib
+            self._C, self._L = C, _lib.shim()
+            self.flags = symm.empty(self.world, dtype=torch.int64, device=self.val.device)
+            self.flags.zero_()
+            torch.cuda.synchronize()
+            fh = symm.rendezvous(self.flags, group=grp)
+            self._flag_views = [fh.get_buffer(r, (self.world,), torch.int64) for r in range(self.world)]
+            self.flag_ptrs = torch.tensor([v.data_ptr() for v in self._flag_views], dtype=torch.int64, device=self.val.device)
+            self.epoch = torch.zeros(1, dtype=torch.int64, device=self.val.device)
+            torch.cuda.synchronize()
         except Exception as e:  # pragma: no cover (GPU boxes only)
             self.p2p_error = repr(e)
             ok = 0
@@ -217,8 +229,14 @@ class ShardedCsr:
             self._step += 1
             self.sym[i].copy_(x_shard)
             own.copy_(x_shard)
-            self.hdl[i].barrier(channel=0, timeout_ms=20000)     # every rank's shard i is written (and step k-1 is fully read)
             main = torch.cuda.current_stream()
+            # every rank's shard i is written (and step k-1 is fully read): device-side barrier over NVLink peer memory,
+            # epoch in device memory -> correct on every replay of a captured step; a missing rank traps after 30 s
+            rc = self._L.b200peer_barrier(self._C.c_void_p(main.cuda_stream), self._C.c_void_p(self.flag_ptrs.data_ptr()),
+                                          self._C.c_void_p(self.epoch.data_ptr()), self._C.c_int(self.rank), self._C.c_int(self.world),
+                                          self._C.c_double(30.0))
+            if rc != 0:
+                raise RuntimeError(f"b200peer_barrier failed with code {rc}")
             self.ev_ready.record(main)
             for s in self.copy_streams:
                 s.wait_event(self.ev_ready)
@@ -314,8 +332,8 @@ class ShardedCsr:
             own_call()
             wait()
             remote_call()
-        if graph is None:
-            graph = x_shard.is_cuda and os.environ.get("B200SPMV_STEP_GRAPH", "1") != "0"
+        if graph is None:   # (NCCL inside a captured step measured slower than eager: 247 vs 199 us at N = 2 -- graphs only for p2p)
+            graph = x_shard.is_cuda and self.exchange == "p2p" and os.environ.get("B200SPMV_STEP_GRAPH", "1") != "0"
         if not graph:
             return step
         try:
@@ -365,6 +383,9 @@ class ShardedCsr:
         return replay
 
     def close(self):
+        if getattr(self, "_graphs", None):
+            torch.cuda.synchronize()
+            self._graphs = None
         for name in ("own_op", "remote_op", "local_op"):
             op = getattr(self, name, None)
             if op is not None and hasattr(op, "close"):

@@ -97,6 +97,13 @@ B200SPMV_EXPORT int    b200cg_update_xr(void* stream, int64_t n, double* x, doub
 B200SPMV_EXPORT int    b200cg_update_p(void* stream, int64_t n, double* p, const double* r, const double* delta_new,
                                        const double* delta);
 
+/* Device-side barrier over NVLink peer memory (one process per GPU, one box), graph-replay safe: the epoch lives in device
+ * memory.  peer_flag_ptrs_dev: device array of `world` pointers, entry r = rank r's flag array (`world` 8-byte slots,
+ * zero-initialised, mapped into this process: symmetric memory / CUDA IPC); epoch_dev: one zero-initialised 8-byte counter
+ * in local device memory.  A rank that does not arrive within timeout_seconds makes the kernel trap (CUDA error). */
+B200SPMV_EXPORT int b200peer_barrier(void* stream, const void* peer_flag_ptrs_dev, void* epoch_dev, int my_rank, int world,
+                                     double timeout_seconds);
+
 /* COO (row-sorted or not).  Replaces cusparseSpMV for cusparseCreateCoo descriptors
  * (cuSPARSE/spmv_coo/spmv_coo_example.c:86-104). */
 B200SPMV_EXPORT size_t b200spmv_coo_workspace_bytes(int64_t rows, int64_t nnz);

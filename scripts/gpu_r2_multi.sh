@@ -5,7 +5,7 @@ N=${1:-2}
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi topo -m > $OUT/r2_topo_n$N.txt 2>&1
 run() {  # tag, extra args
-  timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) \
+  BENCH_WATCHDOG_S=150 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) \
      bench.py --gpus $N --steps 50 --warmup 5 $2 > $OUT/r2_n${N}_$1.json 2> $OUT/r2_n${N}_$1.err
   echo "== $1 rc=$?"; tail -n 3 $OUT/r2_n${N}_$1.err | cut -c1-300
   python - <<PY
