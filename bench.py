@@ -40,6 +40,7 @@ UNIT = "GB/s"
 ROWS_PER_GPU = 1_000_000
 AVG_NNZ = 16
 CG_GRID = 8192
+ROW_WEIGHT = 0.0       # N>1: work of a row block = nnz + ROW_WEIGHT * rows (0 = plain nnz balance)
 CG_ITERS = 200
 
 
@@ -455,7 +456,7 @@ def run_ours(args):
     else:
         def make_local(r, c, arrays):
             return cs.SpMVOperator(api, "csr", r, c, arrays, preprocess=True)
-        sh = ShardedCsr(off, col, val, rank, world, make_local, exchange=args.exchange)   # R-MAT rows read every x block
+        sh = ShardedCsr(off, col, val, rank, world, make_local, exchange=args.exchange, row_weight=args.row_weight)   # R-MAT rows read every x block
         del off, col, val
         torch.cuda.empty_cache()
         xs = sh.new_x_shard(x)
@@ -502,6 +503,19 @@ def run_ours(args):
             local_call()
         ms_k, _, _ = time_steps(torch, local_call, args.steps, False)
         kern_ms = ms_k / args.steps
+        # every rank's local product alone, and the exchange alone (what the overlap has to hide)
+        allk = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(allk, torch.tensor([kern_ms * 1e3], dtype=torch.float64, device="cuda"))
+        local["local_product_us_per_rank"] = [round(float(t.item()), 2) for t in allk]
+        local["rows_per_rank"] = [int(b - a) for a, b in zip(sh.bounds.tolist()[:-1], sh.bounds.tolist()[1:])]
+        if sh.panels:
+            def xonly():
+                sh._start_exchange(xs)()
+            for _ in range(3):
+                xonly()
+            ms_x, _, _ = time_steps(torch, xonly, args.steps, True)
+            local["exchange_alone_us"] = round(ms_x / args.steps * 1e3, 2)
+        kern_ms = max(float(t.item()) for t in allk) * 1e-3
     else:
         kern_ms = ms_step
     achieved = kernel_bytes / (kern_ms * 1e-3) / 1e9
@@ -663,6 +677,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--exchange", default="auto", help="N>1: how x is exchanged (auto | allgather | p2p)")
+    ap.add_argument("--row-weight", type=float, default=ROW_WEIGHT, help="N>1: work model of the row partition: nnz + w * rows")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cusparse", action="store_true", help="skip the closed-library comparison legs")
     ap.add_argument("--no-extra", action="store_true", help="skip the north-star and CG legs")

@@ -34,10 +34,17 @@ import torch
 import torch.distributed as dist
 
 
-def split_rows_by_nnz(off: torch.Tensor, world: int) -> torch.Tensor:
-    """Row boundaries R_0=0 <= ... <= R_world=rows with ~equal non-zeros per block (prefix search on rowOff)."""
+def split_rows_by_nnz(off: torch.Tensor, world: int, row_weight: float = 0.0) -> torch.Tensor:
+    """Row boundaries R_0=0 <= ... <= R_world=rows with ~equal WORK per block (prefix search on rowOff).
+
+    work(rows [a, b)) = non-zeros + row_weight * rows: a row costs the kernels something even when it is short or empty
+    (its y entry, its end-of-row reduction), so on skewed matrices a block of many light rows is slower than a block of few
+    heavy rows with the same non-zeros (measured at N = 2 on R-MAT: 1.7 M light rows vs 0.3 M heavy rows).  row_weight = 0
+    is the plain nnz balance of SURVEY.md 8(e); the merge-path view (items = rows + nnz) is row_weight = 1."""
     rows = off.numel() - 1
     o = off.to(torch.int64) - off[0].to(torch.int64)
+    if row_weight:
+        o = o + (torch.arange(rows + 1, dtype=torch.float64, device=off.device) * row_weight).to(torch.int64)
     nnz = int(o[-1].item())
     targets = torch.tensor([(nnz * g) // world for g in range(1, world)], dtype=torch.int64, device=off.device)
     inner = torch.searchsorted(o.contiguous(), targets, right=False).clamp_(0, rows)
@@ -72,14 +79,14 @@ class ShardedCsr:
 
     def __init__(self, off: torch.Tensor, col: torch.Tensor, val: torch.Tensor, rank: int, world: int,
                  make_local_op: Callable[[int, int, dict], Callable], group=None, base: int = 0, balance: str = "nnz",
-                 exchange: str = "auto", overlap: bool = True):
+                 exchange: str = "auto", overlap: bool = True, row_weight: float = 0.0):
         assert base == 0
         self.rank, self.world, self.group = rank, world, group
         n = off.numel() - 1
         self.global_rows = n
         self.global_nnz = int(off[-1].item())
         if balance == "nnz":
-            self.bounds = split_rows_by_nnz(off, world)           # [world+1], identical on every rank
+            self.bounds = split_rows_by_nnz(off, world, row_weight)   # [world+1], identical on every rank
         else:   # "rows": equal row blocks == the x blocks (regular matrices; lets a solver hand y over as the next x)
             blk = max(1, (n + world - 1) // world)
             self.bounds = torch.tensor([min(g * blk, n) for g in range(world + 1)], dtype=torch.int64, device=off.device)
