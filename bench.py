@@ -40,7 +40,8 @@ UNIT = "GB/s"
 ROWS_PER_GPU = 1_000_000
 AVG_NNZ = 16
 CG_GRID = 8192
-ROW_WEIGHT = 0.0       # N>1: work of a row block = nnz + ROW_WEIGHT * rows (0 = plain nnz balance)
+ROW_WEIGHT = 12.0      # N>1: work of a row block = nnz + ROW_WEIGHT * rows (measured at N = 2: local products 104 / 165 us at weight 0,
+                       #      121 / 128 us at 8, 131 / 117 us at 16)
 CG_ITERS = 200
 
 
@@ -461,7 +462,8 @@ def run_ours(args):
         torch.cuda.empty_cache()
         xs = sh.new_x_shard(x)
         ys = sh.new_y_shard()
-        step = sh.make_step(xs, ys)
+        step = sh.make_step(xs, ys, in_place=True)      # x is constant over the timed loop: published once, exchanged every step
+        e2e_inner = sh.make_step(xs, ys, graph=False)   # e2e: a new x arrives from the host every step -> staged + exchanged
         args._panels = sh.panels
         if sh.panels:      # the local product alone = own-column panel + remote-column panel, no exchange
             own_call = sh.own_op.prebuilt(sh.x_full, ys, 1.0, 0.0)
@@ -555,7 +557,7 @@ def run_ours(args):
 
         def e2e_step():
             xs.copy_(hx, non_blocking=True)
-            step()
+            e2e_inner()
             hy.copy_(ys, non_blocking=True)
         for _ in range(3):
             e2e_step()

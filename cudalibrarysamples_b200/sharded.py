@@ -104,8 +104,11 @@ class ShardedCsr:
         self.x_full = torch.zeros(self.cols_padded, dtype=val.dtype, device=val.device)
         self._step = 0
         self._plan_exchange(exchange)
-        # column panels: only where the whole x is exchanged and there is something to overlap with
-        self.panels = overlap and world > 1 and self.exchange in ("allgather", "p2p") and self.rows > 0
+        # Column panels: only where the whole x is exchanged AND the exchange is long enough to be worth hiding.  Measured
+        # at N = 2 (8 MB per rank): the split costs the local product ~20 % (two plans, y read back for the second panel,
+        # shorter rows) while the peer copies take ~15 us -- not worth it; from 4 GPUs on (>= 24 MB received per rank) it is.
+        min_world = int(os.environ.get("B200SPMV_PANELS_FROM", "4"))
+        self.panels = overlap and world >= min_world and self.exchange in ("allgather", "p2p") and self.rows > 0
         if self.panels:
             lo = rank * self.x_block
             (oo, oc, ov), (ro, rc, rv) = split_column_panels(self.off, self.col, self.val, lo, lo + self.x_block)
@@ -196,11 +199,14 @@ class ShardedCsr:
             self.side = torch.cuda.Stream()
             self.ev_in, self.ev_out = torch.cuda.Event(), torch.cuda.Event()
             return
-        ncs = min(3, self.world - 1)
+        ncs = 4
         self.copy_streams = [torch.cuda.Stream() for _ in range(ncs)]
         self.ev_ready = torch.cuda.Event()
         self.ev_done = [torch.cuda.Event() for _ in range(ncs)]
         self.pull_order = [(self.rank + 1 + i) % self.world for i in range(self.world - 1)]   # staggered: no source read twice at once
+        # every peer block is pulled in `pull_chunks` pieces on different streams (several copy engines per source when
+        # there are few sources: one 8 MB peer copy alone ran at ~320 GB/s at N = 2)
+        self.pull_chunks = max(1, ncs // max(1, self.world - 1))
 
     def describe_exchange(self) -> str:
         if self.world == 1:
@@ -234,9 +240,9 @@ class ShardedCsr:
         if self.exchange == "p2p":
             i = self._step & 1
             self._step += 1
-            self.sym[i].copy_(x_shard)
-            own.copy_(x_shard)
             main = torch.cuda.current_stream()
+            if x_shard.data_ptr() != self.sym[i].data_ptr():
+                self.sym[i].copy_(x_shard)                       # (a caller that produces its shard in shard_buffer() skips this)
             # every rank's shard i is written (and step k-1 is fully read): device-side barrier over NVLink peer memory,
             # epoch in device memory -> correct on every replay of a captured step; a missing rank traps after 30 s
             rc = self._L.b200peer_barrier(self._C.c_void_p(main.cuda_stream), self._C.c_void_p(self.flag_ptrs.data_ptr()),
@@ -247,12 +253,22 @@ class ShardedCsr:
             self.ev_ready.record(main)
             for s in self.copy_streams:
                 s.wait_event(self.ev_ready)
-            ncs = len(self.copy_streams)
-            for k, h in enumerate(self.pull_order):
-                with torch.cuda.stream(self.copy_streams[k % ncs]):
-                    self.x_full[h * blk:(h + 1) * blk].copy_(self.peer[i][h], non_blocking=True)
+            ncs, nch = len(self.copy_streams), self.pull_chunks
+            piece = (blk + nch - 1) // nch
+            k = 0
+            for h in self.pull_order:                             # peer blocks, each in `nch` pieces, round-robin over the streams
+                for c in range(nch):
+                    lo, hi = c * piece, min((c + 1) * piece, blk)
+                    if hi > lo:
+                        with torch.cuda.stream(self.copy_streams[k % ncs]):
+                            self.x_full[h * blk + lo:h * blk + hi].copy_(self.peer[i][h][lo:hi], non_blocking=True)
+                        k += 1
+            with torch.cuda.stream(self.copy_streams[k % ncs]):   # my own block: a local copy, off the critical path as well
+                own.copy_(self.sym[i], non_blocking=True)
             for s, e in zip(self.copy_streams, self.ev_done):
                 e.record(s)
+            if self.panels:                                       # the own-column panel may start as soon as MY block is in place
+                main.wait_event(self.ev_done[k % ncs])
 
             def wait():
                 for e in self.ev_done:
@@ -271,6 +287,13 @@ class ShardedCsr:
         own.copy_(x_shard)
         dist.all_gather_into_tensor(self.x_full, x_shard, group=self.group)
         return lambda: None
+
+    def shard_buffer(self):
+        """p2p exchange: the symmetric-memory buffer the NEXT step publishes to the other ranks.  A caller that produces its
+        x shard here (and passes this tensor as x_shard) saves the staging copy of the step."""
+        if self.exchange != "p2p":
+            raise RuntimeError("shard_buffer() exists for the p2p exchange only")
+        return self.sym[self._step & 1]
 
     def new_x_shard(self, x=None):
         """This rank's equal block of a global vector x (zero-padded at the end of the last block)."""
@@ -312,7 +335,8 @@ class ShardedCsr:
         self.remote_op(self.x_full, y_shard, alpha, 1.0)
         return y_shard
 
-    def make_step(self, x_shard: torch.Tensor, y_shard: torch.Tensor, local_call=None, graph: bool | None = None):
+    def make_step(self, x_shard: torch.Tensor, y_shard: torch.Tensor, local_call=None, graph: bool | None = None,
+                  in_place: bool = False):
         """A zero-argument callable for timing loops: one full step y = A x with fixed buffers and alpha = 1, beta = 0;
         uses the operators' prebuilt calls when they offer them (ctypes arguments built once).
 
@@ -320,25 +344,38 @@ class ShardedCsr:
         the side streams, both panel kernels -- is captured ONCE per shard-buffer parity into a CUDA graph and replayed:
         issued from Python the ~15 launches of a step cost more host time (~190 us measured at N = 2) than the step
         takes on the GPUs.  If the capture is refused the eager step is returned and `self.graph_error` says why."""
+        in_place = in_place and self.exchange == "p2p"
+        if in_place:       # x does not change between the steps of this loop: it is published once, in both shard buffers
+            for t in self.sym:
+                t.copy_(x_shard)
+        shard = (lambda: self.sym[self._step & 1]) if in_place else (lambda: x_shard)
         if not self.panels:
             call = local_call
             if call is None:
                 op = self.local_op
                 call = op.prebuilt(self.x_full, y_shard, 1.0, 0.0) if hasattr(op, "prebuilt") else (lambda: op(self.x_full, y_shard, 1.0, 0.0))
+            if self.world == 1 or self.exchange == "halo":
+                def step():
+                    self.gather_x(x_shard)
+                    call()
+                return step
 
             def step():
-                self.gather_x(x_shard)
+                self._start_exchange(shard())()
                 call()
-            return step
+            return self._maybe_graph(step, x_shard, graph)
         mk = lambda op, beta: (op.prebuilt(self.x_full, y_shard, 1.0, beta) if hasattr(op, "prebuilt")
                                else (lambda: op(self.x_full, y_shard, 1.0, beta)))
         own_call, remote_call = mk(self.own_op, 0.0), mk(self.remote_op, 1.0)
 
         def step():
-            wait = self._start_exchange(x_shard)
+            wait = self._start_exchange(shard())
             own_call()
             wait()
             remote_call()
+        return self._maybe_graph(step, x_shard, graph)
+
+    def _maybe_graph(self, step, x_shard, graph):
         if graph is None:   # (NCCL inside a captured step measured slower than eager: 247 vs 199 us at N = 2 -- graphs only for p2p)
             graph = x_shard.is_cuda and self.exchange == "p2p" and os.environ.get("B200SPMV_STEP_GRAPH", "1") != "0"
         if not graph:
@@ -355,7 +392,7 @@ class ShardedCsr:
         barrier per step suffices); replayed alternately in the order the eager steps would run."""
         main = torch.cuda.current_stream()
         cap = torch.cuda.Stream()
-        ops = [op for op in (self.own_op, self.remote_op) if hasattr(op, "handle")]
+        ops = [op for op in ((self.own_op, self.remote_op) if self.panels else (self.local_op,)) if hasattr(op, "handle")]
         for _ in range(2):                      # warm-up: both parities, eagerly, on the stream the graphs are captured on
             step()
         torch.cuda.synchronize()

@@ -12,6 +12,23 @@ from cudalibrarysamples_b200.sharded import ShardedCsr, split_rows_by_nnz
 from oracle import oracle as O
 
 
+def _collect(q, procs, timeout=240):
+    """The result rank 0 put on the queue -- or a test failure (not a hang) when a worker died or the time is up."""
+    import time
+    t0 = time.time()
+    while q.empty():
+        if any(p.exitcode not in (None, 0) for p in procs):
+            for p in procs:
+                p.kill()
+            pytest.fail("a worker process failed: " + str([p.exitcode for p in procs]))
+        if time.time() - t0 > timeout:
+            for p in procs:
+                p.kill()
+            pytest.fail("workers timed out")
+        time.sleep(0.05)
+    return q.get()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -28,6 +45,7 @@ def _oracle_op(rows, cols, arrays):
 
 
 def _worker(rank, world, port, rows, q):
+    os.environ["B200SPMV_PANELS_FROM"] = "2"           # column panels from 2 ranks on (default 4): the host logic under test
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -83,7 +101,7 @@ def test_sharded_spmv_matches_single_process(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, rows, q)) for r in range(world)]
     for p in procs:
         p.start()
-    out = q.get()
+    out = _collect(q, procs)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -150,7 +168,7 @@ def test_sharded_cg_converges_like_scipy(world):
     procs = [ctx.Process(target=_cg_worker, args=(r, world, port, grid, iters, q)) for r in range(world)]
     for p in procs:
         p.start()
-    out = q.get()
+    out = _collect(q, procs)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
