@@ -103,6 +103,9 @@ B200SPMV_EXPORT int    b200cg_update_p(void* stream, int64_t n, double* p, const
  * in local device memory.  A rank that does not arrive within timeout_seconds makes the kernel trap (CUDA error). */
 B200SPMV_EXPORT int b200peer_barrier(void* stream, const void* peer_flag_ptrs_dev, void* epoch_dev, int my_rank, int world,
                                      double timeout_seconds);
+/* dst[0, bytes) = src[0, bytes) with `ctas` CTAs of 256 threads, 16-byte loads / stores (both pointers 16-byte aligned):
+ * the SM-side pull of a peer's x shard over NVLink. */
+B200SPMV_EXPORT int b200peer_pull(void* stream, void* dst, const void* src, size_t bytes, int ctas);
 
 /* COO (row-sorted or not).  Replaces cusparseSpMV for cusparseCreateCoo descriptors
  * (cuSPARSE/spmv_coo/spmv_coo_example.c:86-104). */
