@@ -456,7 +456,13 @@ def run_ours(args):
         exchange = None
     else:
         def make_local(r, c, arrays):
-            return cs.SpMVOperator(api, "csr", r, c, arrays, preprocess=True)
+            # remote-column panels run with beta = 1: csr_flat_kernel then touches non-empty rows only (no per-row pass),
+            # which is what a panel with mostly empty rows wants -- forced on for them, row-statistic choice for the rest
+            api.set_option("B200SPMV_FLAT", "on" if arrays.get("role") == "remote" else "auto")
+            try:
+                return cs.SpMVOperator(api, "csr", r, c, arrays, preprocess=True)
+            finally:
+                api.set_option("B200SPMV_FLAT", "auto")
         sh = ShardedCsr(off, col, val, rank, world, make_local, exchange=args.exchange, row_weight=args.row_weight)   # R-MAT rows read every x block
         del off, col, val
         torch.cuda.empty_cache()
@@ -465,13 +471,11 @@ def run_ours(args):
         step = sh.make_step(xs, ys, in_place=True)      # x is constant over the timed loop: published once, exchanged every step
         e2e_inner = sh.make_step(xs, ys, graph=False)   # e2e: a new x arrives from the host every step -> staged + exchanged
         args._panels = sh.panels
-        if sh.panels:      # the local product alone = own-column panel + remote-column panel, no exchange
-            own_call = sh.own_op.prebuilt(sh.x_full, ys, 1.0, 0.0)
-            remote_call = sh.remote_op.prebuilt(sh.x_full, ys, 1.0, 1.0)
-
+        args._npanels = len(sh.panel_ops) if sh.panels else 1
+        if sh.panels:      # the local product alone = all column panels back to back, no exchange
             def local_call():
-                own_call()
-                remote_call()
+                for c in sh.panel_calls:
+                    c()
         else:
             local_call = sh.local_op.prebuilt(sh.x_full, ys, 1.0, 0.0)
         exchange = sh.describe_exchange()
@@ -630,7 +634,7 @@ def run_ours(args):
 
     if rank == 0:
         launches = {"b200::csr_flat_kernel<double>": 2, "b200::csr_seg_kernel<double>": 2, "b200::csr_tile_kernel<double>": 2,
-                    "b200::csr_rowwise_kernel<double>": 2}.get(kname, 1) * (2 if dist_on and getattr(args, "_panels", False) else 1)
+                    "b200::csr_rowwise_kernel<double>": 2}.get(kname, 1) * (getattr(args, "_npanels", 1) if dist_on else 1)
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

@@ -398,7 +398,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) csr_flat_fixup_kernel(const FlatArgs<T> a, long long nctas) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const T alpha = a.s.a(), beta = a.s.b();
-    if (t < a.rows) {
+    if (t < a.rows && beta != T(1)) {                       // beta == 1 (a later column panel of a sharded product): y stays as it is
         if (__ldg(a.off + t) == __ldg(a.off + t + 1)) flat_store_y(a.y + t, alpha, T(0), beta);
     }
     if (t >= nctas - 1) return;
@@ -442,7 +442,9 @@ static int launch_flat(cudaStream_t stream, int64_t rows, int64_t nnz, const voi
     csr_flat_kernel<T><<<(unsigned)nctas, FLAT_BLOCK, 0, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    const int64_t work = rows > nctas - 1 ? rows : nctas - 1;                    // empty rows + CTA-crossing rows
+    // empty rows + CTA-crossing rows; with a host-side beta == 1 the empty rows need no pass at all
+    const bool skip_rows = !on_device && *(const T*)beta == T(1);
+    const int64_t work = (!skip_rows && rows > nctas - 1) ? rows : (nctas - 1 > 0 ? nctas - 1 : 1);
     csr_flat_fixup_kernel<T><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(a, (long long)nctas);
     return (int)cudaGetLastError();
 }

@@ -66,6 +66,25 @@ def split_column_panels(off: torch.Tensor, col: torch.Tensor, val: torch.Tensor,
     return (off_own, col[own].contiguous(), val[own].contiguous()), (off_rem, col[rem].contiguous(), val[rem].contiguous())
 
 
+def split_column_groups(off: torch.Tensor, col: torch.Tensor, val: torch.Tensor, blk: int, groups):
+    """One CSR per group of x blocks: groups = [[b0, b1, ...], ...] (block ids, every block in exactly one group); the g-th
+    result holds the entries whose column block  col // blk  belongs to groups[g].  Row and column order are kept."""
+    nblocks = sum(len(g) for g in groups)
+    owner = torch.empty(nblocks, dtype=torch.int64, device=col.device)
+    for gi, g in enumerate(groups):
+        for b in g:
+            owner[b] = gi
+    gid = owner[torch.div(col.to(torch.int64), blk, rounding_mode="floor")]
+    o64 = off.to(torch.int64) - off[0].to(torch.int64)
+    out = []
+    for gi in range(len(groups)):
+        sel = gid == gi
+        cs = torch.zeros(col.numel() + 1, dtype=torch.int64, device=col.device)
+        cs[1:] = torch.cumsum(sel.to(torch.int64), 0)
+        out.append((cs[o64].to(torch.int32).contiguous(), col[sel].contiguous(), val[sel].contiguous()))
+    return out
+
+
 class ShardedCsr:
     """This rank's row block of a global square CSR matrix plus the exchange plan for x.
 
@@ -109,15 +128,27 @@ class ShardedCsr:
         # shorter rows) while the peer copies take ~15 us -- not worth it; from 4 GPUs on (>= 24 MB received per rank) it is.
         min_world = int(os.environ.get("B200SPMV_PANELS_FROM", "4"))
         self.panels = overlap and world >= min_world and self.exchange in ("allgather", "p2p") and self.rows > 0
+        # blocks in the order they arrive (staggered: rank r pulls r+1, r+2, ... so that no source is read twice at once)
+        self.pull_order = [(rank + 1 + i) % world for i in range(world - 1)]
         if self.panels:
-            lo = rank * self.x_block
-            (oo, oc, ov), (ro, rc, rv) = split_column_panels(self.off, self.col, self.val, lo, lo + self.x_block)
-            self.own_nnz, self.remote_nnz = int(oc.numel()), int(rc.numel())
-            self.own_op = make_local_op(self.rows, self.cols_padded, dict(off=oo, col=oc, val=ov))
-            self.remote_op = make_local_op(self.rows, self.cols_padded, dict(off=ro, col=rc, val=rv))
-            self.local_op = self.remote_op            # (kept for callers that close "the" local operator)
+            # own block first, then the remote blocks in arrival order, in at most 3 groups (larger groups last: the later
+            # a group, the more of the exchange is already behind it)
+            ng = min(world - 1, int(os.environ.get("B200SPMV_REMOTE_GROUPS", "3")))
+            base, extra = divmod(world - 1, ng)
+            sizes = [base + (1 if i >= ng - extra else 0) for i in range(ng)]
+            self.panel_groups, k = [[rank]], 0
+            for sz in sizes:
+                self.panel_groups.append(self.pull_order[k:k + sz])
+                k += sz
+            parts = split_column_groups(self.off, self.col, self.val, self.x_block, self.panel_groups)
+            self.panel_nnz = [int(c.numel()) for (_, c, _) in parts]
+            self.own_nnz, self.remote_nnz = self.panel_nnz[0], sum(self.panel_nnz[1:])
+            self.panel_ops = [make_local_op(self.rows, self.cols_padded, dict(off=o, col=c, val=v, role="own" if gi == 0 else "remote"))
+                              for gi, (o, c, v) in enumerate(parts)]
+            self.own_op, self.remote_op = self.panel_ops[0], self.panel_ops[-1]
+            self.local_op = self.panel_ops[-1]        # (kept for callers that close "the" local operator)
         else:
-            self.local_op = make_local_op(self.rows, self.cols_padded, dict(off=self.off, col=self.col, val=self.val))
+            self.local_op = make_local_op(self.rows, self.cols_padded, dict(off=self.off, col=self.col, val=self.val, role="whole"))
         if self.exchange == "p2p":
             self._init_p2p()
         elif self.exchange == "allgather" and val.is_cuda and world > 1:
@@ -199,14 +230,13 @@ class ShardedCsr:
             self.side = torch.cuda.Stream()
             self.ev_in, self.ev_out = torch.cuda.Event(), torch.cuda.Event()
             return
-        ncs = 4
-        self.copy_streams = [torch.cuda.Stream() for _ in range(ncs)]
-        self.ev_ready = torch.cuda.Event()
-        self.ev_done = [torch.cuda.Event() for _ in range(ncs)]
-        self.pull_order = [(self.rank + 1 + i) % self.world for i in range(self.world - 1)]   # staggered: no source read twice at once
-        # every peer block is pulled in `pull_chunks` pieces on different streams (several copy engines per source when
-        # there are few sources: one 8 MB peer copy alone ran at ~320 GB/s at N = 2)
-        self.pull_chunks = max(1, ncs // max(1, self.world - 1))
+        # Two copy streams, blocks issued IN ARRIVAL ORDER alternately on them: measured at N = 2 one copy-engine peer copy of
+        # 8 MB runs at ~340 GB/s and splitting it over more streams does not help, so two copies in flight fill most of the
+        # 900 GB/s NVLink ingress while the early blocks still land early (the panel pipeline below feeds on that).
+        self.copy_streams = [torch.cuda.Stream() for _ in range(2)]
+        self.own_stream = torch.cuda.Stream()
+        self.ev_ready, self.ev_own = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_block = [torch.cuda.Event() for _ in range(self.world - 1)]
 
     def describe_exchange(self) -> str:
         if self.world == 1:
@@ -220,7 +250,8 @@ class ShardedCsr:
             how += "; the whole step replayed as a CUDA graph"
         if self.panels:
             how += (f"; overlapped with the own-column panel of the local product ({self.own_nnz} of {self.nnz} local non-zeros), "
-                    "the remote-column panel follows with beta = 1")
+                    f"then {len(self.panel_groups) - 1} remote-column panel(s) in arrival order of their x blocks {self.panel_groups[1:]} "
+                    "with beta = 1")
         return how
 
     # ------------------------------------------------------------------------------------------------ exchange
@@ -234,7 +265,8 @@ class ShardedCsr:
                 w.wait()
 
     def _start_exchange(self, x_shard: torch.Tensor):
-        """Kick off the assembly of x_full; returns a function that makes the current stream wait for it."""
+        """Kick off the assembly of x_full; returns the waits: one callable per panel (or a single one without panels) that
+        makes the current stream wait until the x blocks of that panel are in place."""
         blk = self.x_block
         own = self.x_full[self.rank * blk:(self.rank + 1) * blk]
         if self.exchange == "p2p":
@@ -251,29 +283,18 @@ class ShardedCsr:
             if rc != 0:
                 raise RuntimeError(f"b200peer_barrier failed with code {rc}")
             self.ev_ready.record(main)
+            self.own_stream.wait_event(self.ev_ready)
+            with torch.cuda.stream(self.own_stream):              # my own block: a local copy next to the peer copies
+                own.copy_(self.sym[i], non_blocking=True)
+                self.ev_own.record(self.own_stream)
             for s in self.copy_streams:
                 s.wait_event(self.ev_ready)
-            ncs, nch = len(self.copy_streams), self.pull_chunks
-            piece = (blk + nch - 1) // nch
-            k = 0
-            for h in self.pull_order:                             # peer blocks, each in `nch` pieces, round-robin over the streams
-                for c in range(nch):
-                    lo, hi = c * piece, min((c + 1) * piece, blk)
-                    if hi > lo:
-                        with torch.cuda.stream(self.copy_streams[k % ncs]):
-                            self.x_full[h * blk + lo:h * blk + hi].copy_(self.peer[i][h][lo:hi], non_blocking=True)
-                        k += 1
-            with torch.cuda.stream(self.copy_streams[k % ncs]):   # my own block: a local copy, off the critical path as well
-                own.copy_(self.sym[i], non_blocking=True)
-            for s, e in zip(self.copy_streams, self.ev_done):
-                e.record(s)
-            if self.panels:                                       # the own-column panel may start as soon as MY block is in place
-                main.wait_event(self.ev_done[k % ncs])
-
-            def wait():
-                for e in self.ev_done:
-                    main.wait_event(e)
-            return wait
+            for k, h in enumerate(self.pull_order):               # peer blocks in arrival order, alternating over two streams
+                st = self.copy_streams[k & 1]
+                with torch.cuda.stream(st):
+                    self.x_full[h * blk:(h + 1) * blk].copy_(self.peer[i][h], non_blocking=True)
+                    self.ev_block[k].record(st)
+            return self._p2p_waits(main)
         if self.exchange == "allgather" and hasattr(self, "side"):
             main = torch.cuda.current_stream()
             own.copy_(x_shard)
@@ -282,11 +303,31 @@ class ShardedCsr:
             with torch.cuda.stream(self.side):
                 dist.all_gather_into_tensor(self.x_full, x_shard, group=self.group)
                 self.ev_out.record(self.side)
-            return lambda: main.wait_event(self.ev_out)
+            w = lambda: main.wait_event(self.ev_out)
+            return [lambda: None] + [w] * (len(self.panel_groups) - 1) if self.panels else [w]
         # CPU (gloo tests) / no side stream: blocking exchange
         own.copy_(x_shard)
         dist.all_gather_into_tensor(self.x_full, x_shard, group=self.group)
-        return lambda: None
+        return [lambda: None] * (len(self.panel_groups) if self.panels else 1)
+
+    def _p2p_waits(self, main):
+        """One wait per panel (own block, then each group of remote blocks), or a single wait for everything."""
+        def wait_blocks(ks):
+            def w():
+                for k in ks:
+                    main.wait_event(self.ev_block[k])
+            return w
+        if not self.panels:
+            def wall():
+                main.wait_event(self.ev_own)
+                for e in self.ev_block:
+                    main.wait_event(e)
+            return [wall]
+        waits, k = [lambda: main.wait_event(self.ev_own)], 0
+        for g in self.panel_groups[1:]:
+            waits.append(wait_blocks(list(range(k, k + len(g)))))
+            k += len(g)
+        return waits
 
     def shard_buffer(self):
         """p2p exchange: the symmetric-memory buffer the NEXT step publishes to the other ranks.  A caller that produces its
@@ -319,7 +360,8 @@ class ShardedCsr:
         elif self.exchange == "halo":
             self._halo_exchange(x_shard)
         else:
-            self._start_exchange(x_shard)()
+            for w in self._start_exchange(x_shard):
+                w()
         return self.x_full
 
     def spmv(self, x_shard: torch.Tensor, y_shard: torch.Tensor, alpha=1.0, beta=0.0) -> torch.Tensor:
@@ -329,10 +371,10 @@ class ShardedCsr:
             if self.rows > 0:
                 self.local_op(self.x_full, y_shard, alpha, beta)
             return y_shard
-        wait = self._start_exchange(x_shard)
-        self.own_op(self.x_full, y_shard, alpha, beta)            # needs only this rank's own x block
-        wait()
-        self.remote_op(self.x_full, y_shard, alpha, 1.0)
+        waits = self._start_exchange(x_shard)
+        for gi, (w, op) in enumerate(zip(waits, self.panel_ops)):  # own panel first; every later panel adds to y (beta = 1)
+            w()
+            op(self.x_full, y_shard, alpha, beta if gi == 0 else 1.0)
         return y_shard
 
     def make_step(self, x_shard: torch.Tensor, y_shard: torch.Tensor, local_call=None, graph: bool | None = None,
@@ -361,18 +403,19 @@ class ShardedCsr:
                 return step
 
             def step():
-                self._start_exchange(shard())()
+                for w in self._start_exchange(shard()):
+                    w()
                 call()
             return self._maybe_graph(step, x_shard, graph)
         mk = lambda op, beta: (op.prebuilt(self.x_full, y_shard, 1.0, beta) if hasattr(op, "prebuilt")
-                               else (lambda: op(self.x_full, y_shard, 1.0, beta)))
-        own_call, remote_call = mk(self.own_op, 0.0), mk(self.remote_op, 1.0)
+                               else (lambda op=op: op(self.x_full, y_shard, 1.0, beta)))
+        calls = [mk(op, 0.0 if gi == 0 else 1.0) for gi, op in enumerate(self.panel_ops)]
+        self.panel_calls = calls
 
         def step():
-            wait = self._start_exchange(shard())
-            own_call()
-            wait()
-            remote_call()
+            for w, call in zip(self._start_exchange(shard()), calls):
+                w()
+                call()
         return self._maybe_graph(step, x_shard, graph)
 
     def _maybe_graph(self, step, x_shard, graph):
@@ -392,7 +435,7 @@ class ShardedCsr:
         barrier per step suffices); replayed alternately in the order the eager steps would run."""
         main = torch.cuda.current_stream()
         cap = torch.cuda.Stream()
-        ops = [op for op in ((self.own_op, self.remote_op) if self.panels else (self.local_op,)) if hasattr(op, "handle")]
+        ops = [op for op in (self.panel_ops if self.panels else (self.local_op,)) if hasattr(op, "handle")]
         for _ in range(2):                      # warm-up: both parities, eagerly, on the stream the graphs are captured on
             step()
         torch.cuda.synchronize()
@@ -430,7 +473,6 @@ class ShardedCsr:
         if getattr(self, "_graphs", None):
             torch.cuda.synchronize()
             self._graphs = None
-        for name in ("own_op", "remote_op", "local_op"):
-            op = getattr(self, name, None)
+        for op in (self.panel_ops if self.panels else [self.local_op]):
             if op is not None and hasattr(op, "close"):
                 op.close()
