@@ -96,3 +96,58 @@ def test_config4_poisson_8192_fp64_csr(env):
     b = spmv(cs, ours, "csr", n, n, arrays, torch.ones(n, dtype=torch.float64, device="cuda"), alpha=0.75)
     interior = b.view(g, g)[1:-1, 1:-1]
     assert float((interior - 0.75 * 0.04).abs().max().item()) < 1e-13
+
+
+def test_north_star_rmat_10m_fp64_csr(env):
+    """BASELINE.json north_star acceptance size: R-MAT 10,000,000 x 10,000,000, avg 16 nnz/row, fp64;
+    ||y - y_ref|| / ||y_ref|| < 1e-12 against the closed library, through the preprocessed call sequence of
+    spmv_csr_example.c:104-112 (the flat plan's 31-bit non-zero positions and > 2^27 non-zeros are exercised here)."""
+    cs, W, ours, closed = env
+    rows = 10_000_000
+    off, col, val = W.rmat_csr(rows)
+    assert int(col.numel()) > 150_000_000
+    arrays = dict(off=off, col=col, val=val)
+    x1, x2 = W.uniform(44, rows), W.uniform(45, rows)
+    ours.reset_stats()
+    y1 = spmv(cs, ours, "csr", rows, rows, arrays, x1)
+    assert ours.stats()["forwarded"] == 0
+    assert rel(y1, spmv(cs, closed, "csr", rows, rows, arrays, x1)) < 1e-12
+    y2 = spmv(cs, ours, "csr", rows, rows, arrays, x2)
+    y12 = spmv(cs, ours, "csr", rows, rows, arrays, 0.5 * x1 - 2.0 * x2)
+    assert rel(y12, 0.5 * y1 - 2.0 * y2) < 1e-12
+    # the no-preprocess path (cg_example.c style: tile plan rebuilt per call) on the same matrix
+    op = cs.SpMVOperator(ours, "csr", rows, rows, arrays, preprocess=False)
+    y3 = torch.zeros(rows, dtype=torch.float64, device="cuda")
+    op(x1, y3, 1.0, 0.0)
+    torch.cuda.synchronize()
+    op.close()
+    assert rel(y3, y1) < 1e-13
+    assert torch.equal(y1, spmv(cs, ours, "csr", rows, rows, arrays, x1))      # bit-reproducible
+
+
+def test_config5_spmm_2m_fp32_csr_times_dense(env):
+    """BASELINE.json configs[4]: fp32 CSR SpMM (cuSPARSE/spmm_csr), A 2M x 2M with 32 non-zeros per row, B dense n = 64,
+    column-major B and C as in spmm_csr_example.c:100-104; against the closed library on the same buffers, plus
+    linearity in B and the column-by-column identity  C[:, j] = SpMV(A, B[:, j])."""
+    cs, W, ours, closed = env
+    rows, per_row, n = 2_000_000, 32, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    col = torch.randint(0, rows, (rows, per_row), device="cuda", generator=g, dtype=torch.int32).sort(dim=1).values.reshape(-1).contiguous()
+    off = (torch.arange(rows + 1, device="cuda", dtype=torch.int64) * per_row).to(torch.int32)
+    val = W.uniform(43, rows * per_row, torch.float32)
+    arrays = dict(off=off, col=col, val=val)
+    B1, B2 = W.uniform(46, rows * n, torch.float32), W.uniform(47, rows * n, torch.float32)
+    C0 = torch.zeros(rows * n, dtype=torch.float32, device="cuda")
+    ours.reset_stats()
+    c1 = cs.spmm(ours, rows, rows, arrays, B1, C0)
+    assert ours.stats()["forwarded"] == 0
+    ref = cs.spmm(closed, rows, rows, arrays, B1, C0)
+    assert rel(c1, ref) < 1e-5
+    del ref
+    c12 = cs.spmm(ours, rows, rows, arrays, 0.5 * B1 - 2.0 * B2, C0)
+    c2 = cs.spmm(ours, rows, rows, arrays, B2, C0)
+    assert rel(c12, 0.5 * c1 - 2.0 * c2) < 1e-5
+    del c12, c2
+    for j in (0, 37, 63):                                                      # column j of C is one SpMV
+        yj = spmv(cs, ours, "csr", rows, rows, arrays, B1[j * rows:(j + 1) * rows].contiguous())
+        assert rel(c1[j * rows:(j + 1) * rows], yj) < 1e-5
