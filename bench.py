@@ -16,6 +16,7 @@ Extra keys of the line (VERDICT r1 "make the measurement contract complete"):
   north_star_10m    the north-star acceptance config (R-MAT 10M x 16, fp64): us, GB/s, fraction of peak, error vs cuSPARSE
   cg_config4        BASELINE.json configs[3]: CG, 5-pt Poisson 8192^2, 200 iterations, row-sharded over the N GPUs: iterations/s
   cusparse_toolkit  the closed library of the CUDA 12.9 toolkit (the one the reference samples link), timed by a C harness
+  other_configs     BASELINE.json configs[2] (fp32 SELL 7-pt 256^3) and configs[4] (fp32 CSR x dense, n = 64), N = 1 only
 """
 from __future__ import annotations
 
@@ -335,6 +336,68 @@ def north_star_leg(torch, cs, W, api, peak, steps):
     return out
 
 
+def other_configs_leg(torch, cs, W, api, peak):
+    """BASELINE.json configs[2] and configs[4] on one GPU, ours and the closed library (torch-bundled copy) on the same buffers:
+    fp32 Sliced-ELL SpMV on the 7-pt Laplacian 256^3, and fp32 CSR x dense (2M x 2M, 32 non-zeros per row, n = 64,
+    column-major B / C as in spmm_csr_example.c:100-104)."""
+    out = {}
+    closed = cs.Api("cusparse")
+
+    def timed(fn, steps):
+        for _ in range(3):
+            fn()
+        ms, _, _ = time_steps(torch, fn, steps, False)
+        return ms * 1e3 / steps
+
+    # ---- configs[2]: fp32 SELL, 7-pt 3D Laplacian 256^3, slice 32
+    nx = 256
+    n = nx ** 3
+    off, col, val = W.laplace7_csr(nx, torch.float32)
+    so, sc, sv = W.csr_to_sell(off, col, val, 32)
+    nbytes = W.sell_bytes(n, n, int(sv.numel()), int(so.numel()) - 1, 4)
+    arrays = dict(off=so, col=sc, val=sv, slice_size=32, nnz=int(col.numel()))
+    x = W.uniform(44, n, torch.float32)
+    res, ys = {"workload": f"fp32 Sliced-ELL (slice 32) SpMV, 7-pt Laplacian {nx}^3 ({n} rows, {int(col.numel())} non-zeros)", "algorithmic_bytes": nbytes}, {}
+    for name, a in (("ours", api), ("cusparse_torch_bundled", closed)):
+        op = cs.SpMVOperator(a, "sell", n, n, arrays)
+        y = torch.zeros(n, dtype=torch.float32, device="cuda")
+        us = timed(op.prebuilt(x, y, 1.0, 0.0), 50)
+        res[name] = {"us_per_spmv": round(us, 2), "value": round(nbytes / us / 1e3, 1), "unit": UNIT, "frac_of_peak": round(nbytes / us / 1e3 / peak, 4)}
+        ys[name] = y
+        op.close()
+    res["rel_err_vs_cusparse"] = float((torch.linalg.norm(ys["ours"].double() - ys["cusparse_torch_bundled"].double()) / torch.linalg.norm(ys["cusparse_torch_bundled"].double())).item())
+    out["config3_sell_f32_laplace7_256"] = res
+    del off, col, val, so, sc, sv, arrays, x, ys
+    torch.cuda.empty_cache()
+
+    # ---- configs[4]: fp32 CSR x dense
+    rows, per_row, nn = 2_000_000, 32, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    col = torch.randint(0, rows, (rows, per_row), device="cuda", generator=g, dtype=torch.int32).sort(dim=1).values.reshape(-1).contiguous()
+    off = (torch.arange(rows + 1, device="cuda", dtype=torch.int64) * per_row).to(torch.int32)
+    val = W.uniform(43, rows * per_row, torch.float32)
+    arrays = dict(off=off, col=col, val=val)
+    B = W.uniform(46, rows * nn, torch.float32)
+    C0 = torch.zeros(rows * nn, dtype=torch.float32, device="cuda")
+    nbytes = rows * per_row * 8 + (rows + 1) * 4 + 2 * rows * nn * 4
+    res, cs_out = {"workload": f"fp32 CSR x dense, A {rows}x{rows} with {per_row} uniformly random non-zeros per row, B {rows}x{nn} and C column-major, "
+                               "alpha=1, beta=0; single GPU (BASELINE.json quotes 8 GPUs: row blocks of A and C with B replicated)",
+                   "algorithmic_bytes": nbytes, "flops": 2 * rows * per_row * nn}, {}
+    for name, a in (("ours", api), ("cusparse_torch_bundled", closed)):
+        ts = []
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            cs_out[name] = cs.spmm(a, rows, rows, arrays, B, C0, 1.0, 0.0, timing=(e0, e1))
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = sorted(ts[1:])[1]
+        res[name] = {"us_per_spmm": round(us, 1), "gflops": round(res["flops"] / us / 1e3, 1), "value": round(nbytes / us / 1e3, 1), "unit": UNIT,
+                     "frac_of_peak": round(nbytes / us / 1e3 / peak, 4)}
+    res["rel_err_vs_cusparse"] = float((torch.linalg.norm(cs_out["ours"].double() - cs_out["cusparse_torch_bundled"].double()) / torch.linalg.norm(cs_out["cusparse_torch_bundled"].double())).item())
+    out["config5_spmm_f32_2m_n64"] = res
+    return out
+
+
 def cg_leg(torch, dist, cs, W, api, rank, world):
     """BASELINE.json configs[3]: CG, fp64, 5-pt Poisson 8192^2 (cg_example.c:71-128 generator), 200 fixed iterations,
     row-sharded over the N GPUs (strong scaling), iterations/s = 200 / max-over-ranks device time."""
@@ -631,6 +694,13 @@ def run_ours(args):
             cg = cg_leg(torch, dist, cs, W, api, rank, world)
         except Exception as e:  # pragma: no cover
             cg = {"error": repr(e)}
+    others = None
+    if not dist_on and not args.no_extra:
+        torch.cuda.empty_cache()
+        try:
+            others = other_configs_leg(torch, cs, W, api, peak)
+        except Exception as e:  # pragma: no cover
+            others = {"error": repr(e)}
 
     if rank == 0:
         launches = {"b200::csr_flat_kernel<double>": 2, "b200::csr_seg_kernel<double>": 2, "b200::csr_tile_kernel<double>": 2,
@@ -646,7 +716,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": kernel_bytes, "peak_source": peak_src,
                          "per_rank": local},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches * args.steps, "clocks": clocks,
-            "cusparse_same_box": closed, "cusparse_toolkit": toolkit, "north_star_10m": north, "cg_config4": cg,
+            "cusparse_same_box": closed, "cusparse_toolkit": toolkit, "north_star_10m": north, "cg_config4": cg, "other_configs": others,
             "exchange": exchange, "forwarded_calls_in_timed_region": stats_hot["forwarded"], "impl": "b200",
         }
         prof = os.path.join(ROOT, "profiles", "traffic.json")

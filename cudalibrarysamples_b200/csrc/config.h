@@ -12,6 +12,7 @@ struct Config {
     int sell_generic = 0;   // B200SPMV_SELL_GENERIC = 1: never use the slice-32 specialisation
     int flat        = -1;   // B200SPMV_FLAT = auto|on|off: the preprocess-built flat CSR plan (csr_flat_kernel); auto = by the matrix' row statistic
     int flat_quiet_permille = 350;   // B200SPMV_FLAT_QUIET: auto picks the flat kernel when at least this share of the 32-non-zero steps ends no row
+    int short_rows  = -1;   // B200SPMV_SHORT = auto|on|off: csr_short_kernel (warp per 32 rows); auto = preprocess found no row longer than 32
     int coo_kernel  = -1;   // B200SPMV_COO_KERNEL = tile|seg ; -1 = default (seg)
 };
 

@@ -116,6 +116,7 @@ struct MatInfo {
     cudaDataType         vtype = CUDA_R_32F;
     int64_t              sell_values_size = 0, slice_size = 0;
     bool                 use_flat = false;       // preprocess built the flat plan and the row statistic favours csr_flat_kernel
+    bool                 use_short = false;      // preprocess found no row longer than b200spmv_csr_short_max_row(): csr_short_kernel
     void*                plan_buffer = nullptr;  // externalBuffer holding this matrix' CSR plan: set ONLY by cusparseSpMV_preprocess
 };
 struct VecInfo {
@@ -183,8 +184,12 @@ void record_mat(const void* d, const MatInfo& m) {
 inline int dtype_of(cudaDataType t) { return t == CUDA_R_32F ? 0 : (t == CUDA_R_64F ? 1 : -1); }
 
 // Can our kernels take this call?  (Everything else is forwarded to the real library.)
-bool supported(cusparseOperation_t op, const MatInfo& m, const VecInfo& x, const VecInfo& y, cudaDataType compute) {
+bool supported(cusparseOperation_t op, const MatInfo& m, const VecInfo& x, const VecInfo& y, cudaDataType compute, cusparseSpMVAlg_t alg) {
     if (op != CUSPARSE_OPERATION_NON_TRANSPOSE) return false;
+    // CUSPARSE_SPMV_COO_ALG2 promises bit-wise reproducible results (cusparse.h:5668-5677, cusparseSpMVAlg_t); our COO kernels add runs that
+    // cross warps with floating-point atomics, so that request stays with the closed library.  (CSR / SELL kernels here are
+    // reproducible for every alg value.)
+    if (m.format == CUSPARSE_FORMAT_COO && alg == CUSPARSE_SPMV_COO_ALG2) return false;
     if (dtype_of(m.vtype) < 0 || x.vtype != m.vtype || y.vtype != m.vtype || compute != m.vtype) return false;
     if (m.off_type != CUSPARSE_INDEX_32I || m.col_type != CUSPARSE_INDEX_32I) return false;
     if (m.format != CUSPARSE_FORMAT_CSR && m.format != CUSPARSE_FORMAT_COO && m.format != CUSPARSE_FORMAT_SLICED_ELLPACK) return false;
@@ -212,10 +217,13 @@ static bool flat_eligible(const MatInfo& m) {
     return m.nnz > 0 && mode != 0 && (mode == 1 || m.nnz >= 8 * m.rows);
 }
 static size_t flat_plan_offset(const MatInfo& m) { return (b200spmv_csr_workspace_bytes(m.rows, m.nnz) + 255) / 256 * 256; }
-static size_t csr_buffer_bytes(const MatInfo& m) {
+static size_t csr_plans_bytes(const MatInfo& m) {
     return flat_eligible(m) ? flat_plan_offset(m) + b200spmv_csr_flat_workspace_bytes(m.rows, m.nnz)
                             : b200spmv_csr_workspace_bytes(m.rows, m.nnz);
 }
+// ... then one 256-byte slot for the statistics preprocess reads back (longest row)
+static size_t csr_stat_offset(const MatInfo& m) { return (csr_plans_bytes(m) + 255) / 256 * 256; }
+static size_t csr_buffer_bytes(const MatInfo& m) { return csr_stat_offset(m) + 256; }
 
 extern "C" {
 
@@ -329,6 +337,7 @@ cusparseStatus_t cusparseCsrSetPointers(cusparseSpMatDescr_t d, void* off, void*
             it->second.offsets = off; it->second.col_ind = col; it->second.values = val;
             it->second.plan_buffer = nullptr;  // structure may have changed: re-analyse on the next SpMV
             it->second.use_flat = false;
+            it->second.use_short = false;
         }
     }
     return st;
@@ -405,7 +414,7 @@ cusparseStatus_t cusparseSpMV_bufferSize(cusparseHandle_t handle, cusparseOperat
     size_t real_size = 0;
     cusparseStatus_t st = R.cusparseSpMV_bufferSize(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, &real_size);
     MatInfo m; VecInfo x, y;
-    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType)) {
+    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType, alg)) {
         *bufferSize = real_size;
         return st;
     }
@@ -449,7 +458,7 @@ cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t handle, cusparseOperat
     if (R.forward) return R.cusparseSpMV_preprocess(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
     if (!handle || !matA || !vecX || !vecY) return CUSPARSE_STATUS_INVALID_VALUE;
     MatInfo m; VecInfo x, y;
-    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType))
+    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType, alg))
         return R.cusparseSpMV_preprocess(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
     if (x.size != m.cols || y.size != m.rows) return CUSPARSE_STATUS_INVALID_VALUE;
     if (m.format != CUSPARSE_FORMAT_CSR) return CUSPARSE_STATUS_SUCCESS;  // COO / SELL need no analysis
@@ -464,10 +473,10 @@ cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t handle, cusparseOperat
     // which no row ends (R-MAT 1M: 69 %, uniform 16 per row or stencils: 0 %).  Reading the statistic back synchronises
     // the stream once, here in preprocess; while the stream is being captured the read-back is skipped and the tile
     // kernels stay in charge.
-    bool use_flat = false;
+    bool use_flat = false, use_short = false;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusNone;
     if (flat_eligible(m)) {
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusNone;
         if (cap == cudaStreamCaptureStatusNone) {
             char* fws = (char*)externalBuffer + flat_plan_offset(m);
             int rc = b200spmv_csr_flat_analyze((void*)stream, m.rows, m.nnz, m.offsets, (int32_t)m.base, fws);
@@ -485,10 +494,24 @@ cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t handle, cusparseOperat
                                ctl[2], use_flat ? "csr_flat_kernel" : "tile kernels");
         }
     }
+    // All rows short (stencils, meshes)?  The longest row decides; same one-time read-back as above.
+    const int short_mode = b200::config().short_rows;
+    if (!use_flat && short_mode != 0 && m.nnz > 0 && cap == cudaStreamCaptureStatusNone) {
+        int32_t* stat = (int32_t*)((char*)externalBuffer + csr_stat_offset(m));
+        int rc = b200spmv_csr_max_row_length((void*)stream, m.rows, m.offsets, stat);
+        if (rc != 0) return to_status(rc);
+        int32_t longest = 0;
+        if (cudaMemcpyAsync(&longest, stat, sizeof longest, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+            cudaStreamSynchronize(stream) != cudaSuccess)
+            return CUSPARSE_STATUS_EXECUTION_FAILED;
+        use_short = short_mode == 1 || longest <= b200spmv_csr_short_max_row();
+        if (R.log) fprintf(stderr, "[b200spmv] longest row: %d non-zeros -> %s\n", (int)longest, use_short ? "csr_short_kernel" : "tile kernels");
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_mats.find((const void*)matA);
     if (it != g_mats.end()) {
         it->second.use_flat = use_flat;
+        it->second.use_short = use_short;
         it->second.plan_buffer = externalBuffer;
         g_plan_owner[externalBuffer] = it->second.uid;     // a buffer holds one matrix' plan: the latest preprocess wins
     }
@@ -506,7 +529,7 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
     }
     if (!handle || !matA || !vecX || !vecY || !alpha || !beta) return CUSPARSE_STATUS_INVALID_VALUE;
     MatInfo m; VecInfo x, y;
-    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType)) {
+    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType, alg)) {
         if (R.log) fprintf(stderr, "[b200spmv] SpMV forwarded to libcusparse (unsupported combination)\n");
         b200::stats().forwarded_calls++;
         return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
@@ -535,6 +558,13 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
             logf("SpMV csr_flat_kernel", m);
             rc = b200spmv_csr_flat_mv((void*)stream, dt, m.rows, m.cols, m.nnz, m.offsets, m.col_ind, m.values, (int32_t)m.base, alpha, beta,
                                       on_dev, x.values, (void*)y.values, (char*)externalBuffer + flat_plan_offset(m));
+            b200::stats().native_calls++;
+            return to_status(rc);
+        }
+        if (trusted && m.use_short) {
+            logf("SpMV csr_short_kernel", m);
+            rc = b200spmv_csr_short_mv((void*)stream, dt, m.rows, m.cols, m.nnz, m.offsets, m.col_ind, m.values, (int32_t)m.base, alpha,
+                                       beta, on_dev, x.values, (void*)y.values);
             b200::stats().native_calls++;
             return to_status(rc);
         }

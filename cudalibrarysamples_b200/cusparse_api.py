@@ -316,7 +316,7 @@ class SpMVOperator:
 
 
 def spmm(api: Api, rows: int, cols: int, arrays: dict, B: torch.Tensor, C0: torch.Tensor, alpha=1.0, beta=0.0,
-         order_b: int = CUSPARSE_ORDER_COL, order_c: int = CUSPARSE_ORDER_COL, base: int = 0) -> torch.Tensor:
+         order_b: int = CUSPARSE_ORDER_COL, order_c: int = CUSPARSE_ORDER_COL, base: int = 0, timing=None) -> torch.Tensor:
     """The call sequence of cuSPARSE/spmm_csr/spmm_csr_example.c:86-132 once: C = alpha*A*B + beta*C0.
 
     B and C0 are 1-D device buffers holding the cols x n / rows x n matrices in the given order with the tight leading
@@ -333,7 +333,11 @@ def spmm(api: Api, rows: int, cols: int, arrays: dict, B: torch.Tensor, C0: torc
     size = api.cusparseSpMM_bufferSize(h, op, op, alpha, matA, matB, beta, matC, ct)
     buf = torch.empty(max(size, 16), dtype=torch.uint8, device=val.device)
     api.cusparseSpMM_preprocess(h, op, op, alpha, matA, matB, beta, matC, ct, CUSPARSE_SPMM_ALG_DEFAULT, buf)
+    if timing is not None:          # (start, stop) CUDA events around the cusparseSpMM call alone (scripts/bench_formats.py)
+        timing[0].record()
     api.cusparseSpMM(h, op, op, alpha, matA, matB, beta, matC, ct, CUSPARSE_SPMM_ALG_DEFAULT, buf)
+    if timing is not None:
+        timing[1].record()
     torch.cuda.synchronize()
     api.cusparseDestroySpMat(matA)
     api.cusparseDestroyDnMat(matB)

@@ -75,6 +75,17 @@ B200SPMV_EXPORT int    b200spmv_csr_flat_mv(void* stream, int dtype, int64_t row
 B200SPMV_EXPORT void   b200spmv_csr_flat_plan_offsets(int64_t rows, int64_t nnz, size_t* endmask, size_t* chunk_run,
                                                       size_t* nzrow, size_t* ctl);
 
+/* CSR, all rows short (spmv_csr_short.cu): a warp per 32 consecutive rows, products staged in the warp's own slice of
+ * shared memory, one lane per row adds them up; needs no plan, only the caller's row offsets.  cusparseSpMV_preprocess picks
+ * it when the longest row (b200spmv_csr_max_row_length, written to device memory) has at most b200spmv_csr_short_max_row()
+ * non-zeros -- the stencil operators of cuSPARSE/cg/cg_example.c:71-128 and cuSPARSE/bicgstab/bicgstab_example.c:69-127. */
+B200SPMV_EXPORT int    b200spmv_csr_short_max_row(void);
+B200SPMV_EXPORT int    b200spmv_csr_max_row_length(void* stream, int64_t rows, const void* row_offsets, int32_t* out_device);
+B200SPMV_EXPORT int    b200spmv_csr_short_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz,
+                                             const void* row_offsets, const void* col_ind, const void* values,
+                                             int32_t base, const void* alpha, const void* beta, int scalars_on_device,
+                                             const void* x, void* y);
+
 /* CSR x dense: C = alpha*A*B + beta*C, A rows x cols (CSR, int32 indices), B cols x n, C rows x n, each dense matrix row- or
  * column-major with leading dimension ld* (elements).  Replaces cusparseSpMM for CSR descriptors, opA = opB = NON_TRANSPOSE
  * (cuSPARSE/spmm_csr/spmm_csr_example.c:105-132).  No workspace. */

@@ -47,7 +47,7 @@ def case(name, fmt, rows, cols, arrays, nbytes, dtype, out):
 
 
 out = {}
-which = sys.argv[1:] or ["sell", "cg", "coo", "f32"]
+which = sys.argv[1:] or ["sell", "cg", "coo", "f32", "spmm"]
 if "sell" in which:
     nx = 256
     off, col, val = W.laplace7_csr(nx, torch.float32)
@@ -74,5 +74,36 @@ if "coo" in which or "f32" in which:
         case("coo_f64_rmat1m", "coo", rows, rows, dict(row=row, col=col, val=val), W.coo_bytes(rows, rows, int(col.numel()), 8), torch.float64, out)
     if "f32" in which:
         case("csr_f32_rmat1m", "csr", rows, rows, dict(off=off, col=col, val=val.float()), W.csr_bytes(rows, rows, int(col.numel()), 4), torch.float32, out)
+if "spmm" in which:
+    # BASELINE.json configs[4] on one GPU: fp32 CSR x dense, A 2M x 2M with 32 non-zeros per row, n = 64
+    rows, per_row, n = 2_000_000, 32, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    col = torch.randint(0, rows, (rows, per_row), device="cuda", generator=g, dtype=torch.int32).sort(dim=1).values.reshape(-1).contiguous()
+    off = (torch.arange(rows + 1, device="cuda", dtype=torch.int64) * per_row).to(torch.int32)
+    val = W.uniform(43, rows * per_row, torch.float32)
+    arrays = dict(off=off, col=col, val=val)
+    B = W.uniform(46, rows * n, torch.float32)
+    C0 = torch.zeros(rows * n, dtype=torch.float32, device="cuda")
+    nbytes = rows * per_row * 8 + (rows + 1) * 4 + 2 * rows * n * 4          # A once, B once, C written once
+    for order, oname in ((cs.CUSPARSE_ORDER_COL, "colmajor"), (cs.CUSPARSE_ORDER_ROW, "rowmajor")):
+        res, cs_out = {}, {}
+        for impl in ("b200", "cusparse"):
+            api = cs.Api(impl)
+            ts = []
+            for rep in range(4):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                out_c = cs.spmm(api, rows, rows, arrays, B, C0, 1.0, 0.0, order, order, timing=(e0, e1))
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            cs_out[impl] = out_c
+            us = sorted(ts[1:])[len(ts[1:]) // 2]
+            res[impl] = dict(us=round(us, 1), gbs=round(nbytes / us / 1e3, 1), gflops=round(2.0 * rows * per_row * n / us / 1e3, 1))
+        res["rel_diff"] = float((torch.linalg.norm(cs_out["b200"].double() - cs_out["cusparse"].double()) / torch.linalg.norm(cs_out["cusparse"].double())).item())
+        res["alg_MB"] = round(nbytes / 1e6, 1)
+        res["speedup_vs_cusparse"] = round(res["cusparse"]["us"] / res["b200"]["us"], 3)
+        print("config5_spmm_f32_2m_n64_" + oname, json.dumps(res), flush=True)
+        out["config5_spmm_f32_2m_n64_" + oname] = res
+        del cs_out
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "bench_formats.json"), "w"), indent=1)

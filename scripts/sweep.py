@@ -100,14 +100,27 @@ if os.environ.get("SWEEP_SET") == "flat":
                 [(10, 4, 4, 8, 0), (10, 4, 4, 8, 1), (12, 4, 4, 8, 1), (8, 4, 4, 8, 1), (10, 2, 4, 8, 1),
                  (10, 4, 4, 16, 1), (12, 4, 4, 16, 1), (8, 4, 4, 16, 1), (20, 4, 2, 16, 1), (10, 4, 2, 32, 1), (20, 4, 2, 32, 1),
                  (5, 4, 8, 8, 1), (20, 4, 2, 8, 1), (40, 4, 1, 16, 1), (40, 4, 1, 8, 1)]}
+if os.environ.get("SWEEP_SET") == "flat2":
+    # csr_flat_kernel, empty rows scaled by the chunk post-pass: (resident CTAs, batch, warps per CTA, steps per warp chunk, look-back)
+    VARIANTS = {f"flat2_occ{o}_k{k}_w{w}_s{st}_lb{lb}": dict(FLAT=(o, k, w, st, lb)) for (o, k, w, st, lb) in
+                [(10, 4, 4, 8, 1), (10, 4, 4, 8, 0), (9, 4, 4, 8, 1), (9, 4, 4, 8, 0), (12, 4, 4, 8, 1), (5, 4, 8, 8, 1), (5, 4, 8, 8, 0),
+                 (10, 4, 4, 16, 1), (10, 4, 4, 16, 0), (8, 4, 4, 8, 0)]}
+if os.environ.get("SWEEP_SET") == "short":
+    # csr_short_kernel: (warps per CTA, load steps per pass, resident CTAs)
+    VARIANTS = {f"short_w{w}_s{st}_occ{o}": dict(SHORT=(w, st, o)) for (w, st, o) in
+                [(8, 8, 5), (8, 8, 4), (8, 8, 6), (4, 8, 10), (4, 8, 8), (8, 6, 6), (8, 6, 8), (16, 8, 2), (8, 12, 4), (8, 16, 3)]}
 if os.environ.get("SWEEP_SET") == "ablate":
     VARIANTS = dict(ABL, t2048_b256_k4_occ6=VARIANTS["t2048_b256_k4_occ6"])
 
 
 def flags(v):
     if "FLAT" in v:
-        o, k, w, st, nz = v["FLAT"]
-        return [f"-DB200_FLAT_MIN_CTAS={o}", f"-DB200_FLAT_BATCH={k}", f"-DB200_FLAT_WARPS={w}", f"-DB200_FLAT_STEPS={st}", f"-DB200_FLAT_NZPRE={nz}"]
+        o, k, w, st = v["FLAT"][:4]
+        lb = v["FLAT"][4] if len(v["FLAT"]) > 4 else 1
+        return [f"-DB200_FLAT_MIN_CTAS={o}", f"-DB200_FLAT_BATCH={k}", f"-DB200_FLAT_WARPS={w}", f"-DB200_FLAT_STEPS={st}", f"-DB200_FLAT_LOOKBACK={lb}"]
+    if "SHORT" in v:
+        w, st, o = v["SHORT"]
+        return [f"-DB200_SHORT_WARPS={w}", f"-DB200_SHORT_STEPS={st}", f"-DB200_SHORT_MIN_CTAS={o}"]
     if "SEG" in v:
         o, k, staged = v["SEG"]
         base = dict(TILE=v.get("TILE", 2048), LONG=v.get("LONG", 512), BLOCK=v.get("BLOCK", 256), BATCH=4, MIN=5)
@@ -137,7 +150,7 @@ def build():
         out = os.path.join(VDIR, f"libb200spmv_{tag}.so")
         b.build_native(extra_flags=flags(v), out_path=out, tag="v_" + tag)
         log = open(os.path.join(ROOT, "cudalibrarysamples_b200", "build", "v_" + tag, "build.log")).read()
-        i = log.find("csr_flat_kernelIdEE") if "FLAT" in v else log.find("csr_seg_kernelIdEE") if "SEG" in v else log.find("csr_rowwise_kernelIdEE") if "RW" in v else log.find("csr_ws_kernelIdEE") if "WS" in v else max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
+        i = log.find("csr_short_kernelIdEE") if "SHORT" in v else log.find("csr_flat_kernelIdEE") if "FLAT" in v else log.find("csr_seg_kernelIdEE") if "SEG" in v else log.find("csr_rowwise_kernelIdEE") if "RW" in v else log.find("csr_ws_kernelIdEE") if "WS" in v else max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
         regs = log[i:i + 400].split("Used ")[1].split(",")[0] if i >= 0 else "?"
         print(tag, regs)
 
@@ -145,6 +158,9 @@ def build():
 def make_workload(name):
     import torch
     from cudalibrarysamples_b200 import workloads as W
+    if name.endswith("_f32"):                                  # same structure, fp32 values
+        rows, off, col, val = make_workload(name[:-4])
+        return rows, off, col, val.float()
     if name.startswith("rmat"):
         rows = {"rmat1m": 1_000_000, "rmat10m": 10_000_000, "rmat4m": 4_000_000, "rmat250k": 250_000}[name]
         off, col, val = W.rmat_csr(rows)
@@ -175,12 +191,12 @@ def run(workloads, variants=None, steps=100):
     libs = [("default", None)] + [(t, os.path.join(VDIR, f"libb200spmv_{t}.so")) for t in VARIANTS if (variants is None or t in variants)]
     libs = [(t, p) for t, p in libs if p is None or os.path.exists(p)]
     if os.environ.get("SWEEP_SET") == "kernels":     # every CSR kernel of the default library, picked through b200spmv_set_option
-        libs = [("default", None)] + [("kernel:" + k, None) for k in ("flat", "tile", "pipe", "seg", "seg:48", "rowwise")]
+        libs = [("default", None)] + [("kernel:" + k, None) for k in ("flat", "short", "tile", "pipe", "seg", "seg:48", "rowwise")]
     for wl in workloads:
         rows, off, col, val = make_workload(wl)
         nnz = int(col.numel())
-        x = W.uniform(44, rows)
-        nbytes = W.csr_bytes(rows, rows, nnz, 8)
+        x = W.uniform(44, rows, val.dtype)
+        nbytes = W.csr_bytes(rows, rows, nnz, val.element_size())
         ref = None
         print(f"== {wl}: rows={rows} nnz={nnz} alg_bytes={nbytes / 1e6:.1f} MB", flush=True)
         for tag, path in libs + [("cusparse", "closed")]:
@@ -188,10 +204,11 @@ def run(workloads, variants=None, steps=100):
             if tag != "cusparse":
                 parts = tag.split(":") if tag.startswith("kernel:") else ["", "auto"]
                 api.set_option("B200SPMV_FLAT", "on" if parts[1] == "flat" else "auto" if parts[1] == "auto" else "off")
-                api.set_option("B200SPMV_CSR_KERNEL", "auto" if parts[1] == "flat" else parts[1])
+                api.set_option("B200SPMV_SHORT", "on" if parts[1] == "short" else "auto" if parts[1] == "auto" else "off")
+                api.set_option("B200SPMV_CSR_KERNEL", "auto" if parts[1] in ("flat", "short") else parts[1])
                 api.set_option("B200SPMV_SEG_DENSE", parts[2] if len(parts) > 2 else "24")
             op = cs.SpMVOperator(api, "csr", rows, rows, dict(off=off, col=col, val=val))
-            y = torch.zeros(rows, dtype=torch.float64, device="cuda")
+            y = torch.zeros(rows, dtype=val.dtype, device="cuda")
             for _ in range(5):
                 op(x, y, 1.0, 0.0)
             torch.cuda.synchronize()
@@ -204,7 +221,7 @@ def run(workloads, variants=None, steps=100):
             us = e0.elapsed_time(e1) * 1e3 / steps
             if ref is None:
                 ref = y.clone()
-            err = float((torch.linalg.norm(y - ref) / torch.linalg.norm(ref)).item())
+            err = float((torch.linalg.norm(y.double() - ref.double()) / torch.linalg.norm(ref.double())).item())
             print(f"  {tag:24s} {us:9.2f} us  {nbytes / us / 1e3:8.1f} GB/s  relerr_vs_first {err:.1e}", flush=True)
             results.setdefault(wl, {})[tag] = dict(us=us, gbs=nbytes / us / 1e3, err=err)
             op.close()

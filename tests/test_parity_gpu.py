@@ -244,21 +244,25 @@ def test_csr_base_one(cs, b200, closed, dtype):
     assert relerr(got.cpu().numpy(), lib.cpu().numpy()) < TOL[dtype]
 
 
-@pytest.fixture(params=["tile", "pipe", "ws", "rowwise", "seg", "seg:1", "seg:1000000", "flat"])
+@pytest.fixture(params=["tile", "pipe", "ws", "rowwise", "seg", "seg:1", "seg:1000000", "flat", "short"])
 def csr_kernel(request, b200):
     """Every CSR kernel variant of the library must give the same answers (b200spmv_set_option picks one).
     "seg:N" = csr_seg_kernel with the row-sparse threshold N: 1 sends every tile that has non-zeros down the register
     path (multi-row steps, > 32 row ends per step), 1000000 sends every tile down the staged-product path.
     "flat" = csr_flat_kernel on the preprocess-built flat plan, forced for every matrix with non-zeros (calls without
-    cusparseSpMV_preprocess still take the tile kernels: the flat plan is only ever built by preprocess)."""
+    cusparseSpMV_preprocess still take the tile kernels: the flat plan is only ever built by preprocess).
+    "short" = csr_short_kernel (a warp per 32 rows) forced for every preprocessed matrix, whatever its row lengths: rows
+    longer than the warp's product buffer go through its multi-pass path."""
     name, _, dense = request.param.partition(":")
     b200.set_option("B200SPMV_FLAT", "on" if name == "flat" else "off")
-    b200.set_option("B200SPMV_CSR_KERNEL", "auto" if name == "flat" else name)
+    b200.set_option("B200SPMV_SHORT", "on" if name == "short" else "off")
+    b200.set_option("B200SPMV_CSR_KERNEL", "auto" if name in ("flat", "short") else name)
     b200.set_option("B200SPMV_SEG_DENSE", dense or "24")
     yield request.param
     b200.set_option("B200SPMV_CSR_KERNEL", "auto")
     b200.set_option("B200SPMV_SEG_DENSE", "24")
     b200.set_option("B200SPMV_FLAT", "auto")
+    b200.set_option("B200SPMV_SHORT", "auto")
 
 
 @pytest.fixture(params=["tile", "seg"])
@@ -720,6 +724,34 @@ def test_flat_kernel_is_chosen_for_skewed_rows_only(cs, b200):
     assert "csr_flat_kernel" not in b200.last_csr_kernel()
 
 
+def test_short_kernel_is_chosen_when_every_row_is_short(cs, b200):
+    """auto: preprocess reads the longest row back; stencils (cg_example.c:71-128) go to csr_short_kernel, R-MAT never does,
+    and a call without cusparseSpMV_preprocess (cg_example.c itself) stays on the plan-per-call tile kernels."""
+    off, col, val = O.gen_stencil5(300)
+    n = 300 * 300
+    xs, ys = O.uniform(5, n), O.uniform(6, n)
+    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
+    want = O.spmv_csr(off, col, val, xs, ys, 0.75, 0.5)
+    got = run(cs, b200, "csr", n, n, arrays, dev(xs), dev(ys), 0.75, 0.5)
+    assert "csr_short_kernel" in b200.last_csr_kernel()
+    assert relerr(got.cpu().numpy(), want) < 1e-13
+    got = run(cs, b200, "csr", n, n, arrays, dev(xs), dev(ys), 0.75, 0.5, preprocess=False)
+    assert "csr_short_kernel" not in b200.last_csr_kernel()
+    assert relerr(got.cpu().numpy(), want) < 1e-12
+    # one row of 33 non-zeros among the short ones: not eligible any more
+    lens = np.full(5000, 5); lens[1234] = 33
+    off, col, val = lens_to_csr(lens, 20000, 9)
+    x, y0 = O.uniform(1, 20000), O.uniform(2, 5000)
+    got = run(cs, b200, "csr", 5000, 20000, dict(off=dev(off), col=dev(col), val=dev(val)), dev(x), dev(y0), 1.0, 0.0)
+    assert "csr_short_kernel" not in b200.last_csr_kernel()
+    assert relerr(got.cpu().numpy(), O.spmv_csr(off, col, val, x, y0, 1.0, 0.0)) < 1e-12
+    lens[1234] = 32
+    off, col, val = lens_to_csr(lens, 20000, 9)
+    got = run(cs, b200, "csr", 5000, 20000, dict(off=dev(off), col=dev(col), val=dev(val)), dev(x), dev(y0), 1.0, 0.0)
+    assert "csr_short_kernel" in b200.last_csr_kernel()
+    assert relerr(got.cpu().numpy(), O.spmv_csr(off, col, val, x, y0, 1.0, 0.0)) < 1e-12
+
+
 def test_device_generators_are_bit_identical_to_the_oracle():
     from cudalibrarysamples_b200 import workloads as W
     off, col, val = W.rmat_csr(30000, avg_nnz=16, seed=42, val_seed=43)
@@ -738,3 +770,25 @@ def test_device_generators_are_bit_identical_to_the_oracle():
         for a, b in zip(W.csr_to_sell(dev(off), dev(col), dev(val), ss), O.csr_to_sell(off, col, val, ss)):
             assert np.array_equal(a.cpu().numpy(), b)
     assert np.array_equal(W.csr_to_coo_rows(dev(off)).cpu().numpy(), O.csr_to_coo_rows(off))
+
+
+def test_coo_alg2_keeps_its_reproducibility_promise(cs, b200):
+    """CUSPARSE_SPMV_COO_ALG2 = "provides deterministic (bit-wise) results for each run" (cusparse.h, cusparseSpMVAlg_t):
+    our COO kernels use floating-point atomics, so that request is handed to the closed library -- counted as a forward."""
+    off, col, val, x, y0 = rmat_case(30000, 16, torch.float64, 77)
+    row = np.repeat(np.arange(30000, dtype=np.int32), np.diff(off))
+    arrays = dict(row=dev(row), col=dev(col), val=dev(val))
+    want = O.spmv_csr(off, col, val, x, y0, 1.0, 0.5)
+    outs = []
+    for _ in range(2):
+        before = b200.stats()
+        op = cs.SpMVOperator(b200, "coo", 30000, 30000, arrays, alg=4)          # CUSPARSE_SPMV_COO_ALG2
+        y = dev(y0).clone()
+        op(dev(x), y, 1.0, 0.5)
+        torch.cuda.synchronize()
+        op.close()
+        after = b200.stats()
+        assert after["forwarded"] == before["forwarded"] + 1 and after["native"] == before["native"]
+        outs.append(y)
+    assert torch.equal(outs[0], outs[1])
+    assert relerr(outs[0].cpu().numpy(), want) < 1e-12
