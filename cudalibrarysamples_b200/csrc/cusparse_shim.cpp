@@ -185,7 +185,9 @@ inline int dtype_of(cudaDataType t) { return t == CUDA_R_32F ? 0 : (t == CUDA_R_
 
 // Can our kernels take this call?  (Everything else is forwarded to the real library.)
 bool supported(cusparseOperation_t op, const MatInfo& m, const VecInfo& x, const VecInfo& y, cudaDataType compute, cusparseSpMVAlg_t alg) {
-    if (op != CUSPARSE_OPERATION_NON_TRANSPOSE) return false;
+    // A^T (== A^H for the real types served here): native for CSR (csr_transpose_kernel) and COO (the COO kernel with the
+    // index arrays swapped); Sliced-ELL transposes stay with the closed library
+    if (op != CUSPARSE_OPERATION_NON_TRANSPOSE && m.format == CUSPARSE_FORMAT_SLICED_ELLPACK) return false;
     // CUSPARSE_SPMV_COO_ALG2 promises bit-wise reproducible results (cusparse.h:5668-5677, cusparseSpMVAlg_t); our COO kernels add runs that
     // cross warps with floating-point atomics, so that request stays with the closed library.  (CSR / SELL kernels here are
     // reproducible for every alg value.)
@@ -460,8 +462,9 @@ cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t handle, cusparseOperat
     MatInfo m; VecInfo x, y;
     if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType, alg))
         return R.cusparseSpMV_preprocess(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
-    if (x.size != m.cols || y.size != m.rows) return CUSPARSE_STATUS_INVALID_VALUE;
-    if (m.format != CUSPARSE_FORMAT_CSR) return CUSPARSE_STATUS_SUCCESS;  // COO / SELL need no analysis
+    const bool tr = opA != CUSPARSE_OPERATION_NON_TRANSPOSE;
+    if (x.size != (tr ? m.rows : m.cols) || y.size != (tr ? m.cols : m.rows)) return CUSPARSE_STATUS_INVALID_VALUE;
+    if (m.format != CUSPARSE_FORMAT_CSR || tr) return CUSPARSE_STATUS_SUCCESS;  // COO / SELL / A^T need no analysis
     if (!externalBuffer || ((uintptr_t)externalBuffer & 15)) return CUSPARSE_STATUS_INVALID_VALUE;
     cudaStream_t stream = nullptr;
     cusparseStatus_t st = R.cusparseGetStream(handle, &stream);
@@ -534,7 +537,8 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
         b200::stats().forwarded_calls++;
         return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
     }
-    if (x.size != m.cols || y.size != m.rows) return CUSPARSE_STATUS_INVALID_VALUE;
+    const bool tr = opA != CUSPARSE_OPERATION_NON_TRANSPOSE;
+    if (x.size != (tr ? m.rows : m.cols) || y.size != (tr ? m.cols : m.rows)) return CUSPARSE_STATUS_INVALID_VALUE;
     cudaStream_t stream = nullptr;
     cusparseStatus_t st = R.cusparseGetStream(handle, &stream);
     if (st != CUSPARSE_STATUS_SUCCESS) return st;
@@ -544,7 +548,15 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
     const int on_dev = pm == CUSPARSE_POINTER_MODE_DEVICE;
     const int dt = dtype_of(m.vtype);
     int rc;
-    if (m.format == CUSPARSE_FORMAT_CSR) {
+    if (tr && m.format == CUSPARSE_FORMAT_CSR) {
+        logf("SpMV csr_transpose_kernel", m);
+        rc = b200spmv_csr_transpose_mv((void*)stream, dt, m.rows, m.cols, m.nnz, m.offsets, m.col_ind, m.values, (int32_t)m.base, alpha,
+                                       beta, on_dev, x.values, (void*)y.values);
+    } else if (tr) {                                        // COO: A^T is the same entry list with the index arrays swapped
+        logf("SpMV coo kernel (transposed: index arrays swapped)", m);
+        rc = b200spmv_coo_mv((void*)stream, dt, m.cols, m.rows, m.nnz, m.col_ind, m.row_ind, m.values, (int32_t)m.base, alpha,
+                             beta, on_dev, x.values, (void*)y.values, externalBuffer);
+    } else if (m.format == CUSPARSE_FORMAT_CSR) {
         if (m.rows == 0) return CUSPARSE_STATUS_SUCCESS;
         if (!externalBuffer || ((uintptr_t)externalBuffer & 15)) {
             // No room for a plan (caller ignored bufferSize): let the real library handle it -- loudly under
@@ -618,8 +630,16 @@ cusparseStatus_t cusparseSpMM_bufferSize(cusparseHandle_t handle, cusparseOperat
                                          const void* alpha, cusparseConstSpMatDescr_t matA, cusparseConstDnMatDescr_t matB,
                                          const void* beta, cusparseDnMatDescr_t matC, cudaDataType computeType,
                                          cusparseSpMMAlg_t alg, size_t* bufferSize) {
-    // our kernel needs no workspace; the real library's answer keeps a forwarded call safe
-    return real().cusparseSpMM_bufferSize(handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg, bufferSize);
+    // the real library's answer keeps a forwarded call safe; ours is the row-major copy of a column-major B
+    Real& R = real();
+    cusparseStatus_t st = R.cusparseSpMM_bufferSize(handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg, bufferSize);
+    MatInfo a; DnMatInfo b, c;
+    if (st == CUSPARSE_STATUS_SUCCESS && !R.forward && bufferSize && handle && matA && matB && matC && find_mat(matA, &a) &&
+        get_dnmat(matB, &b) && get_dnmat(matC, &c) && spmm_supported(opA, opB, a, b, c, computeType)) {
+        const size_t ours = b200spmm_csr_workspace_bytes(dtype_of(a.vtype), b.rows, b.cols, b.order == CUSPARSE_ORDER_ROW);
+        if (ours > *bufferSize) *bufferSize = ours;
+    }
+    return st;
 }
 
 cusparseStatus_t cusparseSpMM_preprocess(cusparseHandle_t handle, cusparseOperation_t opA, cusparseOperation_t opB,
@@ -654,9 +674,10 @@ cusparseStatus_t cusparseSpMM(cusparseHandle_t handle, cusparseOperation_t opA, 
     if (st != CUSPARSE_STATUS_SUCCESS) return st;
     if (R.log) fprintf(stderr, "[b200spmv] SpMM spmm_csr_kernel rows=%lld cols=%lld n=%lld nnz=%lld\n", (long long)a.rows,
                        (long long)a.cols, (long long)c.cols, (long long)a.nnz);
-    const int rc = b200spmm_csr((void*)stream, dtype_of(a.vtype), a.rows, a.cols, c.cols, a.nnz, a.offsets, a.col_ind, a.values,
-                                (int32_t)a.base, alpha, beta, pm == CUSPARSE_POINTER_MODE_DEVICE, b.values, b.ld,
-                                b.order == CUSPARSE_ORDER_ROW, (void*)c.values, c.ld, c.order == CUSPARSE_ORDER_ROW);
+    // externalBuffer: sized by our cusparseSpMM_bufferSize (>= the row-major copy of a column-major B); NULL -> strided walk
+    const int rc = b200spmm_csr_ws((void*)stream, dtype_of(a.vtype), a.rows, a.cols, c.cols, a.nnz, a.offsets, a.col_ind, a.values,
+                                   (int32_t)a.base, alpha, beta, pm == CUSPARSE_POINTER_MODE_DEVICE, b.values, b.ld,
+                                   b.order == CUSPARSE_ORDER_ROW, (void*)c.values, c.ld, c.order == CUSPARSE_ORDER_ROW, externalBuffer);
     b200::stats().native_calls++;
     return to_status(rc);
 }

@@ -235,8 +235,8 @@ class SpMVOperator:
     (cg_example.c:387-418 keeps matA / d_bufferMV for the whole solve and calls cusparseSpMV per iteration)."""
 
     def __init__(self, api: Api, fmt: str, rows: int, cols: int, arrays: dict, base: int = 0, preprocess: bool = True,
-                 alg: int = CUSPARSE_SPMV_ALG_DEFAULT, handle=None):
-        self.api, self.fmt, self.rows, self.cols, self.base, self.alg = api, fmt, rows, cols, base, alg
+                 alg: int = CUSPARSE_SPMV_ALG_DEFAULT, handle=None, op: int = CUSPARSE_OPERATION_NON_TRANSPOSE):
+        self.api, self.fmt, self.rows, self.cols, self.base, self.alg, self.op = api, fmt, rows, cols, base, alg, op
         self.arrays = arrays  # keeps the device tensors alive
         self.own_handle = handle is None
         self.handle = api.cusparseCreate() if handle is None else handle
@@ -255,16 +255,17 @@ class SpMVOperator:
                                                    arrays["off"], arrays["col"], val, base)
         else:
             raise ValueError(fmt)
-        self._x = torch.empty(max(cols, 1), dtype=val.dtype, device=val.device)
-        self._y = torch.empty(max(rows, 1), dtype=val.dtype, device=val.device)
-        self.vecX = api.cusparseCreateDnVec(cols, self._x)
-        self.vecY = api.cusparseCreateDnVec(rows, self._y)
-        size = api.cusparseSpMV_bufferSize(self.handle, CUSPARSE_OPERATION_NON_TRANSPOSE, 1.0, self.mat, self.vecX, 0.0,
+        nx, ny = (cols, rows) if op == CUSPARSE_OPERATION_NON_TRANSPOSE else (rows, cols)      # A^T: y[cols] = A^T x[rows]
+        self._x = torch.empty(max(nx, 1), dtype=val.dtype, device=val.device)
+        self._y = torch.empty(max(ny, 1), dtype=val.dtype, device=val.device)
+        self.vecX = api.cusparseCreateDnVec(nx, self._x)
+        self.vecY = api.cusparseCreateDnVec(ny, self._y)
+        size = api.cusparseSpMV_bufferSize(self.handle, op, 1.0, self.mat, self.vecX, 0.0,
                                            self.vecY, self.ctype, alg)
         self.buffer_bytes = size
         self.buffer = torch.empty(max(size, 16), dtype=torch.uint8, device=val.device)
         if preprocess:
-            api.cusparseSpMV_preprocess(self.handle, CUSPARSE_OPERATION_NON_TRANSPOSE, 1.0, self.mat, self.vecX, 0.0,
+            api.cusparseSpMV_preprocess(self.handle, op, 1.0, self.mat, self.vecX, 0.0,
                                         self.vecY, self.ctype, alg, self.buffer)
 
     def __call__(self, x: torch.Tensor, y: torch.Tensor, alpha=1.0, beta=0.0):
@@ -272,7 +273,7 @@ class SpMVOperator:
         a = self.api
         a.cusparseDnVecSetValues(self.vecX, x)
         a.cusparseDnVecSetValues(self.vecY, y)
-        a.cusparseSpMV(self.handle, CUSPARSE_OPERATION_NON_TRANSPOSE, alpha, self.mat, self.vecX, beta, self.vecY, self.ctype,
+        a.cusparseSpMV(self.handle, self.op, alpha, self.mat, self.vecX, beta, self.vecY, self.ctype,
                        self.alg, self.buffer)
         return y
 
@@ -285,7 +286,7 @@ class SpMVOperator:
         ct = _CT[self.dtype]
         ca, cb = ct(alpha), ct(beta)
         fn = a.lib.cusparseSpMV
-        argv = (self.handle, C.c_int(CUSPARSE_OPERATION_NON_TRANSPOSE), C.cast(C.pointer(ca), C.c_void_p), self.mat, self.vecX,
+        argv = (self.handle, C.c_int(self.op), C.cast(C.pointer(ca), C.c_void_p), self.mat, self.vecX,
                 C.cast(C.pointer(cb), C.c_void_p), self.vecY, C.c_int(self.ctype), C.c_int(self.alg),
                 C.c_void_p(self.buffer.data_ptr()))
         vx, vy, setv = self.vecX, self.vecY, a.lib.cusparseDnVecSetValues

@@ -86,9 +86,23 @@ B200SPMV_EXPORT int    b200spmv_csr_short_mv(void* stream, int dtype, int64_t ro
                                              int32_t base, const void* alpha, const void* beta, int scalars_on_device,
                                              const void* x, void* y);
 
+/* CSR, opA = TRANSPOSE (spmv_csr_transpose.cu): y[cols] = alpha * A^T * x[rows] + beta * y; no plan, no workspace; one
+ * fp atomic per non-zero, so the summation order (not the tolerance) differs between runs. */
+B200SPMV_EXPORT int    b200spmv_csr_transpose_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz,
+                                                 const void* row_offsets, const void* col_ind, const void* values,
+                                                 int32_t base, const void* alpha, const void* beta, int scalars_on_device,
+                                                 const void* x, void* y);
+
 /* CSR x dense: C = alpha*A*B + beta*C, A rows x cols (CSR, int32 indices), B cols x n, C rows x n, each dense matrix row- or
  * column-major with leading dimension ld* (elements).  Replaces cusparseSpMM for CSR descriptors, opA = opB = NON_TRANSPOSE
- * (cuSPARSE/spmm_csr/spmm_csr_example.c:105-132).  No workspace. */
+ * (cuSPARSE/spmm_csr/spmm_csr_example.c:105-132).  b200spmm_csr needs no workspace; b200spmm_csr_ws takes one of
+ * b200spmm_csr_workspace_bytes() bytes (what cusparseSpMM_bufferSize reports, spmm_csr_example.c:105-110) and uses it for a
+ * row-major copy of a column-major B -- the sample's own layout then runs at the row-major speed. */
+B200SPMV_EXPORT size_t b200spmm_csr_workspace_bytes(int dtype, int64_t cols, int64_t n, int b_row_major);
+B200SPMV_EXPORT int b200spmm_csr_ws(void* stream, int dtype, int64_t rows, int64_t cols, int64_t n, int64_t nnz,
+                                    const void* row_offsets, const void* col_ind, const void* values, int32_t base,
+                                    const void* alpha, const void* beta, int scalars_on_device, const void* B, int64_t ldb,
+                                    int b_row_major, void* C, int64_t ldc, int c_row_major, void* workspace);
 B200SPMV_EXPORT int b200spmm_csr(void* stream, int dtype, int64_t rows, int64_t cols, int64_t n, int64_t nnz,
                                  const void* row_offsets, const void* col_ind, const void* values, int32_t base,
                                  const void* alpha, const void* beta, int scalars_on_device, const void* B, int64_t ldb,

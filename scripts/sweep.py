@@ -100,11 +100,9 @@ if os.environ.get("SWEEP_SET") == "flat":
                 [(10, 4, 4, 8, 0), (10, 4, 4, 8, 1), (12, 4, 4, 8, 1), (8, 4, 4, 8, 1), (10, 2, 4, 8, 1),
                  (10, 4, 4, 16, 1), (12, 4, 4, 16, 1), (8, 4, 4, 16, 1), (20, 4, 2, 16, 1), (10, 4, 2, 32, 1), (20, 4, 2, 32, 1),
                  (5, 4, 8, 8, 1), (20, 4, 2, 8, 1), (40, 4, 1, 16, 1), (40, 4, 1, 8, 1)]}
-if os.environ.get("SWEEP_SET") == "flat2":
-    # csr_flat_kernel, empty rows scaled by the chunk post-pass: (resident CTAs, batch, warps per CTA, steps per warp chunk, look-back)
-    VARIANTS = {f"flat2_occ{o}_k{k}_w{w}_s{st}_lb{lb}": dict(FLAT=(o, k, w, st, lb)) for (o, k, w, st, lb) in
-                [(10, 4, 4, 8, 1), (10, 4, 4, 8, 0), (9, 4, 4, 8, 1), (9, 4, 4, 8, 0), (12, 4, 4, 8, 1), (5, 4, 8, 8, 1), (5, 4, 8, 8, 0),
-                 (10, 4, 4, 16, 1), (10, 4, 4, 16, 0), (8, 4, 4, 8, 0)]}
+if os.environ.get("SWEEP_SET") == "flat3":
+    # csr_flat_kernel: (quiet-step ballot, empty rows scaled by tail CTAs of the main grid)
+    VARIANTS = {f"flat3_qb{qb}_et{et}": dict(FLAT3=(qb, et)) for (qb, et) in [(1, 1), (0, 1), (1, 0), (0, 0)]}
 if os.environ.get("SWEEP_SET") == "short":
     # csr_short_kernel: (warps per CTA, load steps per pass, resident CTAs)
     VARIANTS = {f"short_w{w}_s{st}_occ{o}": dict(SHORT=(w, st, o)) for (w, st, o) in
@@ -116,8 +114,9 @@ if os.environ.get("SWEEP_SET") == "ablate":
 def flags(v):
     if "FLAT" in v:
         o, k, w, st = v["FLAT"][:4]
-        lb = v["FLAT"][4] if len(v["FLAT"]) > 4 else 1
-        return [f"-DB200_FLAT_MIN_CTAS={o}", f"-DB200_FLAT_BATCH={k}", f"-DB200_FLAT_WARPS={w}", f"-DB200_FLAT_STEPS={st}", f"-DB200_FLAT_LOOKBACK={lb}"]
+        return [f"-DB200_FLAT_MIN_CTAS={o}", f"-DB200_FLAT_BATCH={k}", f"-DB200_FLAT_WARPS={w}", f"-DB200_FLAT_STEPS={st}"]
+    if "FLAT3" in v:
+        return [f"-DB200_FLAT_QUIET_BALLOT={v['FLAT3'][0]}", f"-DB200_FLAT_EMPTY_TAIL={v['FLAT3'][1]}"]
     if "SHORT" in v:
         w, st, o = v["SHORT"]
         return [f"-DB200_SHORT_WARPS={w}", f"-DB200_SHORT_STEPS={st}", f"-DB200_SHORT_MIN_CTAS={o}"]
@@ -150,7 +149,7 @@ def build():
         out = os.path.join(VDIR, f"libb200spmv_{tag}.so")
         b.build_native(extra_flags=flags(v), out_path=out, tag="v_" + tag)
         log = open(os.path.join(ROOT, "cudalibrarysamples_b200", "build", "v_" + tag, "build.log")).read()
-        i = log.find("csr_short_kernelIdEE") if "SHORT" in v else log.find("csr_flat_kernelIdEE") if "FLAT" in v else log.find("csr_seg_kernelIdEE") if "SEG" in v else log.find("csr_rowwise_kernelIdEE") if "RW" in v else log.find("csr_ws_kernelIdEE") if "WS" in v else max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
+        i = log.find("csr_short_kernelIdEE") if "SHORT" in v else log.find("csr_flat_kernelIdEE") if ("FLAT" in v or "FLAT3" in v) else log.find("csr_seg_kernelIdEE") if "SEG" in v else log.find("csr_rowwise_kernelIdEE") if "RW" in v else log.find("csr_ws_kernelIdEE") if "WS" in v else max(log.find("csr_pipe_kernelIdEE"), log.find("csr_tile_kernelIdEE")) if "-DB200_CSR_KERNEL=0" not in " ".join(flags(v)) else log.find("csr_tile_kernelIdEE")
         regs = log[i:i + 400].split("Used ")[1].split(",")[0] if i >= 0 else "?"
         print(tag, regs)
 

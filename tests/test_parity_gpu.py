@@ -792,3 +792,44 @@ def test_coo_alg2_keeps_its_reproducibility_promise(cs, b200):
         outs.append(y)
     assert torch.equal(outs[0], outs[1])
     assert relerr(outs[0].cpu().numpy(), want) < 1e-12
+
+
+@pytest.mark.parametrize("fmt", ["csr", "coo"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_transposed_spmv_is_native(cs, b200, closed, fmt, dtype):
+    """opA = CUSPARSE_OPERATION_TRANSPOSE (cusparse.h cusparseOperation_t): y[cols] = alpha * A^T x[rows] + beta * y on a
+    rectangular matrix with empty rows, base 1; against the oracle run on the explicitly transposed matrix and against the
+    closed library; served by our kernels (no forward)."""
+    import scipy.sparse as sp
+    rows, cols = 30000, 21000
+    off, col, val, _, _ = rmat_case(rows, 12, dtype, 55)
+    col = (col % cols).astype(np.int32)                          # rectangular: fold the columns (duplicates inside a row are fine)
+    x, y0 = O.uniform(7, rows).astype(val.dtype), O.uniform(8, cols).astype(val.dtype)
+    A = sp.csr_matrix((val.astype(np.float64), col, off), shape=(rows, cols))
+    want = -1.5 * (A.T @ x.astype(np.float64)) + 0.5 * y0.astype(np.float64)
+    if fmt == "csr":
+        arrays = dict(off=dev(off + 1), col=dev(col + 1), val=dev(val))
+    else:
+        row = np.repeat(np.arange(rows, dtype=np.int32), np.diff(off))
+        arrays = dict(row=dev(row + 1), col=dev(col + 1), val=dev(val))
+    outs = {}
+    for name, api in (("ours", b200), ("closed", closed)):
+        before = api.stats() if api.impl == "b200" else None
+        op = cs.SpMVOperator(api, fmt, rows, cols, arrays, base=1, op=cs.CUSPARSE_OPERATION_TRANSPOSE)
+        y = dev(y0).clone()
+        op(dev(x), y, -1.5, 0.5)
+        torch.cuda.synchronize()
+        op.close()
+        if before is not None:
+            after = api.stats()
+            assert after["forwarded"] == before["forwarded"] and after["native"] == before["native"] + 1
+        outs[name] = y.cpu().numpy()
+    assert relerr(outs["ours"], want) < TOL[dtype]
+    assert relerr(outs["ours"], outs["closed"]) < TOL[dtype]
+    # beta = 0 must not read y (NaN-filled), alpha = 1
+    op = cs.SpMVOperator(b200, fmt, rows, cols, arrays, base=1, op=cs.CUSPARSE_OPERATION_TRANSPOSE, preprocess=False)
+    y = torch.full((cols,), float("nan"), dtype=dtype, device="cuda")
+    op(dev(x), y, 1.0, 0.0)
+    torch.cuda.synchronize()
+    op.close()
+    assert relerr(y.cpu().numpy(), A.T @ x.astype(np.float64)) < TOL[dtype]

@@ -92,7 +92,7 @@ def test_column_panels_partition_the_local_matrix():
     assert np.linalg.norm(y - want) <= 1e-13 * np.linalg.norm(want)
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_sharded_spmv_matches_single_process(world):
     rows = 4000
     ctx = mp.get_context("spawn")
