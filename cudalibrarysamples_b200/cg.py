@@ -90,6 +90,8 @@ class FusedCgSolver:
         self.scal = torch.zeros(8, dtype=torch.float64, device=dev)        # [0], [1]: delta of even / odd iterations, [2]: t.p
         self.use_graph = (sh.world == 1 and os.environ.get("B200CG_GRAPH", "1") != "0") if use_graph is None else use_graph
         self.graph_error = None
+        # T = A*P and T . P in one kernel where the local matrix allows it (all rows short: csr_short_kernel's DOT variant)
+        self.fuse_dot = os.environ.get("B200CG_FUSE_DOT", "1") != "0" and hasattr(sh, "can_fuse_dot") and sh.can_fuse_dot()
 
     def _stream(self):
         return self.C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -109,8 +111,13 @@ class FusedCgSolver:
     def _iteration(self, x, r, p, t, cur):
         """one CG iteration; delta_k lives in scal[cur], delta_{k+1} goes to scal[1 - cur]"""
         C, s = self.C, self.scal
-        self.sh.spmv(p, t, alpha=1.0, beta=0.0)                              # T = A * P      (cg_example.c:220-224)
-        self._dot(t, p, s[2:3])                                              # denom = T . P  (:227)
+        if self.fuse_dot:
+            self.sh.spmv_dot(p, t, s[2:3])                                   # T = A * P and denom = T . P in one pass (:220-227)
+            if self.sh.world > 1:
+                dist.all_reduce(s[2:3], group=self.sh.group)
+        else:
+            self.sh.spmv(p, t, alpha=1.0, beta=0.0)                          # T = A * P      (cg_example.c:220-224)
+            self._dot(t, p, s[2:3])                                          # denom = T . P  (:227)
         nxt = 1 - cur
         self._check(self.L.b200cg_update_xr(self._stream(), C.c_int64(self.n), self._p(x), self._p(r), self._p(p), self._p(t),
                                             self._p(s[cur:cur + 1]), self._p(s[2:3]), self._p(s[nxt:nxt + 1]), self._p(self.ws)),
@@ -123,7 +130,10 @@ class FusedCgSolver:
     def run(self, iters: int):
         x = torch.zeros_like(self.b)
         r = self.b.clone()
-        p = r.clone()
+        # the search direction lives inside the assembled x buffer: no staging copy in front of every product
+        own = self.sh.own_x_view() if hasattr(self.sh, "own_x_view") and (self.sh.world == 1 or self.sh.exchange == "halo") else None
+        p = own if own is not None and own.numel() == r.numel() and own.data_ptr() % 16 == 0 else torch.empty_like(r)
+        p.copy_(r)
         t = torch.zeros_like(self.b)
         self._dot(r, r, self.scal[0:1])
         first = self.scal[0:1].clone()
@@ -170,8 +180,10 @@ class FusedCgSolver:
 
     def describe(self) -> str:
         how = "two iterations captured in a CUDA graph and replayed" if self.use_graph and self.graph_error is None else "plain stream launches"
-        return ("CG (cg_example.c:215-287 without the IC(0) preconditioner): SpMV through the C ABI + fused sm_100a BLAS-1 kernels "
-                "(b200cg_dot, b200cg_update_xr = 2 axpy + nrm2 in one pass, b200cg_update_p), all scalars on the device, "
+        spmv = ("T = A*P and T.P in one csr_short_kernel launch (b200spmv_csr_short_mv_dot)" if self.fuse_dot
+                else "SpMV through the C ABI + b200cg_dot")
+        return ("CG (cg_example.c:215-287 without the IC(0) preconditioner): " + spmv + " + fused sm_100a BLAS-1 kernels "
+                "(b200cg_update_xr = 2 axpy + nrm2 in one pass, b200cg_update_p), all scalars on the device, "
                 + how + (f" (graph capture failed: {self.graph_error})" if self.graph_error else ""))
 
 

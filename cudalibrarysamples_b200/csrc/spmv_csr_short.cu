@@ -48,14 +48,21 @@ struct ShortArgs {
     T*         y;
     int        base, rows;
     Scalars<T> s;
+    // DOT variant ("fuse dot(T, P) into the SpMV epilogue", cg_example.c:220-227): *dot_out = sum_i y[i] * w[i]
+    const T*   w;
+    double*    dot_ws;     // one partial per CTA, then the arrival counter
+    double*    dot_out;
 };
 
 __device__ __forceinline__ int short_slot(int i) { return i + (i >> 5); }
 
-template <typename T>
+constexpr int SHORT_MAX_GRID = 148 * (B200_SHORT_MIN_CTAS + 1) * 8;     // launch_short never starts more CTAs than this
+
+template <typename T, bool DOT>
 __global__ void __launch_bounds__(32 * SHORT_WARPS, (sizeof(T) == 8 ? B200_SHORT_MIN_CTAS : B200_SHORT_MIN_CTAS + 1))
 csr_short_kernel(const ShortArgs<T> a) {
     __shared__ T sprod[SHORT_WARPS][SHORT_SLOTS];
+    double dsum = 0.0;                                        // DOT: this lane's share of y . w
     const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
     T* sp = sprod[warp];
     const T alpha = a.s.a(), beta = a.s.b();
@@ -91,7 +98,35 @@ csr_short_kernel(const ShortArgs<T> a) {
             for (int i = lo; i < hi; i++) sum += sp[short_slot(i)];
             __syncwarp();
         }
-        if (live) a.y[row] = axpby(alpha, sum, beta, a.y + row);
+        if (live) {
+            const T yv = axpby(alpha, sum, beta, a.y + row);
+            a.y[row] = yv;
+            if (DOT) dsum += (double)yv * (double)__ldg(a.w + row);
+        }
+    }
+    if (DOT) {
+        // deterministic three-level sum: lanes (butterfly), warps of the CTA (in warp order), CTAs (in CTA order, by the CTA
+        // that arrives last) -- same scheme as csrc/cg_fused.cu
+        __shared__ double swarp[SHORT_WARPS];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        if (lane == 0) swarp[warp] = dsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double part = 0.0;
+#pragma unroll
+            for (int w = 0; w < SHORT_WARPS; w++) part += swarp[w];
+            unsigned* counter = (unsigned*)(a.dot_ws + SHORT_MAX_GRID);
+            a.dot_ws[blockIdx.x] = part;
+            __threadfence();
+            if (atomicAdd(counter, 1u) == gridDim.x - 1) {
+                __threadfence();
+                double t = 0.0;
+                for (unsigned b = 0; b < gridDim.x; b++) t += __ldcg(a.dot_ws + b);
+                *a.dot_out = t;
+                *counter = 0u;
+            }
+        }
     }
 }
 
@@ -107,8 +142,10 @@ __global__ void csr_max_row_kernel(const int* __restrict__ off, int64_t rows, in
 
 template <typename T>
 static int launch_short(cudaStream_t stream, int64_t rows, const void* off, const void* col, const void* val, int base,
-                        const void* alpha, const void* beta, int on_device, const void* x, void* y) {
+                        const void* alpha, const void* beta, int on_device, const void* x, void* y,
+                        const void* w = nullptr, double* dot_out = nullptr, void* dot_ws = nullptr) {
     ShortArgs<T> a;
+    a.w = (const T*)w; a.dot_out = dot_out; a.dot_ws = (double*)dot_ws;
     a.off = (const int*)off; a.col = (const int*)col; a.val = (const T*)val; a.x = (const T*)x; a.y = (T*)y;
     a.base = base; a.rows = (int)rows;
     if (on_device) { a.s.alpha = T(0); a.s.beta = T(0); a.s.alpha_dev = (const T*)alpha; a.s.beta_dev = (const T*)beta; }
@@ -118,7 +155,8 @@ static int launch_short(cudaStream_t stream, int64_t rows, const void* off, cons
     int64_t ctas = (nblocks + SHORT_WARPS - 1) / SHORT_WARPS;
     const int64_t cap = 148LL * (B200_SHORT_MIN_CTAS + (sizeof(T) == 8 ? 0 : 1)) * 8;      // a few waves; beyond that the warps loop
     if (ctas > cap) ctas = cap;
-    csr_short_kernel<T><<<(unsigned)ctas, 32 * SHORT_WARPS, 0, stream>>>(a);
+    if (dot_out) csr_short_kernel<T, true><<<(unsigned)ctas, 32 * SHORT_WARPS, 0, stream>>>(a);
+    else         csr_short_kernel<T, false><<<(unsigned)ctas, 32 * SHORT_WARPS, 0, stream>>>(a);
     return (int)cudaGetLastError();
 }
 
@@ -140,6 +178,25 @@ int b200spmv_csr_max_row_length(void* stream, int64_t rows, const void* row_offs
     if (blocks > 148 * 16) blocks = 148 * 16;
     csr_max_row_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)row_offsets, rows, out_device);
     return (int)cudaGetLastError();
+}
+
+// y = alpha*A*x + beta*y and, in the same pass, *dot_out = y . w (device memory, fp64 accumulation): the T = A*P product of a
+// CG iteration together with its T . P (cg_example.c:220-227).  workspace: b200spmv_csr_short_dot_workspace_bytes(),
+// zeroed once before first use; every call leaves the arrival counter at zero.
+size_t b200spmv_csr_short_dot_workspace_bytes(void) { return (size_t)(SHORT_MAX_GRID + 2) * sizeof(double); }
+
+int b200spmv_csr_short_mv_dot(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz, const void* row_offsets,
+                              const void* col_ind, const void* values, int32_t base, const void* alpha, const void* beta,
+                              int scalars_on_device, const void* x, void* y, const void* w, double* dot_out, void* workspace) {
+    if (rows < 0 || cols < 0 || nnz < 0 || !alpha || !beta || !dot_out || !workspace) return -1;
+    if (rows > INT32_MAX - 64 || nnz > INT32_MAX - 65536) return -1;
+    if (rows > 0 && (!y || !w || !row_offsets || (nnz > 0 && (!col_ind || !values || !x)))) return -1;
+    if (rows == 0) return (int)cudaMemsetAsync(dot_out, 0, sizeof(double), (cudaStream_t)stream);
+    if (dtype == 0)
+        return launch_short<float>((cudaStream_t)stream, rows, row_offsets, col_ind, values, base, alpha, beta, scalars_on_device, x, y, w, dot_out, workspace);
+    if (dtype == 1)
+        return launch_short<double>((cudaStream_t)stream, rows, row_offsets, col_ind, values, base, alpha, beta, scalars_on_device, x, y, w, dot_out, workspace);
+    return -1;
 }
 
 int b200spmv_csr_short_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz, const void* row_offsets,

@@ -255,9 +255,20 @@ class ShardedCsr:
         return how
 
     # ------------------------------------------------------------------------------------------------ exchange
+    def own_x_view(self) -> torch.Tensor:
+        """This rank's block INSIDE the assembled x buffer.  A caller that keeps its x shard here (a CG driver its search
+        direction) saves the staging copy of every product: the exchange then only has to bring in the other blocks."""
+        blk = self.x_block
+        return self.x_full[self.rank * blk:(self.rank + 1) * blk]
+
+    def _stage_own(self, x_shard: torch.Tensor):
+        own = self.own_x_view()
+        if x_shard.data_ptr() != own.data_ptr():
+            own.copy_(x_shard)
+
     def _halo_exchange(self, x_shard: torch.Tensor):
         blk = self.x_block
-        self.x_full[self.rank * blk:(self.rank + 1) * blk].copy_(x_shard)
+        self._stage_own(x_shard)
         ops = [dist.P2POp(dist.isend, x_shard[lo:hi], g, group=self.group) for g, lo, hi in self.send_plan]
         ops += [dist.P2POp(dist.irecv, self.x_full[lo:hi], h, group=self.group) for h, lo, hi in self.recv_plan]
         if ops:
@@ -297,7 +308,8 @@ class ShardedCsr:
             return self._p2p_waits(main)
         if self.exchange == "allgather" and hasattr(self, "side"):
             main = torch.cuda.current_stream()
-            own.copy_(x_shard)
+            if x_shard.data_ptr() != own.data_ptr():
+                own.copy_(x_shard)
             self.ev_in.record(main)
             self.side.wait_event(self.ev_in)
             with torch.cuda.stream(self.side):
@@ -306,7 +318,8 @@ class ShardedCsr:
             w = lambda: main.wait_event(self.ev_out)
             return [lambda: None] + [w] * (len(self.panel_groups) - 1) if self.panels else [w]
         # CPU (gloo tests) / no side stream: blocking exchange
-        own.copy_(x_shard)
+        if x_shard.data_ptr() != own.data_ptr():
+            own.copy_(x_shard)
         dist.all_gather_into_tensor(self.x_full, x_shard, group=self.group)
         return [lambda: None] * (len(self.panel_groups) if self.panels else 1)
 
@@ -356,7 +369,7 @@ class ShardedCsr:
     def gather_x(self, x_shard: torch.Tensor) -> torch.Tensor:
         """The path's single exchange step, complete on return (stream order): x_full holds everything this rank reads."""
         if self.world == 1:
-            self.x_full[:self.x_block].copy_(x_shard)
+            self._stage_own(x_shard)
         elif self.exchange == "halo":
             self._halo_exchange(x_shard)
         else:
@@ -375,6 +388,46 @@ class ShardedCsr:
         for gi, (w, op) in enumerate(zip(waits, self.panel_ops)):  # own panel first; every later panel adds to y (beta = 1)
             w()
             op(self.x_full, y_shard, alpha, beta if gi == 0 else 1.0)
+        return y_shard
+
+    # ------------------------------------------------------------------------------------------------ SpMV + dot (CG)
+    def can_fuse_dot(self) -> bool:
+        """True when y = A x and y . x_shard can run as ONE kernel: the local matrix is whole (no column panels), lives on
+        CUDA, has no row longer than csr_short_kernel takes, and the y rows coincide with this rank's x block (CG)."""
+        if getattr(self, "_fuse_dot", None) is None:
+            ok = (not self.panels) and self.val.is_cuda and self.rows > 0 and (self.rows == self.x_block or self.world == 1)
+            if ok:
+                try:
+                    import ctypes as C
+                    from . import lib as _lib
+                    L = _lib.shim()
+                    L.b200spmv_csr_short_dot_workspace_bytes.restype = C.c_size_t
+                    longest = int((self.off[1:] - self.off[:-1]).max().item())
+                    ok = longest <= int(L.b200spmv_csr_short_max_row())
+                    if ok:
+                        self._dotL, self._dotC = L, C
+                        self._dot_ws = torch.zeros(int(L.b200spmv_csr_short_dot_workspace_bytes()), dtype=torch.uint8, device=self.val.device)
+                except Exception:
+                    ok = False
+            self._fuse_dot = bool(ok)
+        return self._fuse_dot
+
+    def spmv_dot(self, x_shard: torch.Tensor, y_shard: torch.Tensor, dot_out: torch.Tensor) -> torch.Tensor:
+        """y_shard = A[r0:r1, :] @ x  and  dot_out[0] = y_shard . x_shard (this rank's part; fp64, device memory) in one pass
+        over the local matrix: T = A*P together with T . P of a CG iteration (cg_example.c:220-227)."""
+        assert self.can_fuse_dot()
+        C, L = self._dotC, self._dotL
+        self.gather_x(x_shard)
+        one = (C.c_double if self.val.dtype == torch.float64 else C.c_float)(1.0)
+        zero = (C.c_double if self.val.dtype == torch.float64 else C.c_float)(0.0)
+        rc = L.b200spmv_csr_short_mv_dot(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_int(1 if self.val.dtype == torch.float64 else 0),
+                                         C.c_int64(self.rows), C.c_int64(self.cols_padded), C.c_int64(self.nnz),
+                                         C.c_void_p(self.off.data_ptr()), C.c_void_p(self.col.data_ptr()), C.c_void_p(self.val.data_ptr()),
+                                         C.c_int32(0), C.byref(one), C.byref(zero), C.c_int(0), C.c_void_p(self.x_full.data_ptr()),
+                                         C.c_void_p(y_shard.data_ptr()), C.c_void_p(x_shard.data_ptr()), C.c_void_p(dot_out.data_ptr()),
+                                         C.c_void_p(self._dot_ws.data_ptr()))
+        if rc != 0:
+            raise RuntimeError(f"b200spmv_csr_short_mv_dot failed with code {rc}")
         return y_shard
 
     def make_step(self, x_shard: torch.Tensor, y_shard: torch.Tensor, local_call=None, graph: bool | None = None,

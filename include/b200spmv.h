@@ -86,6 +86,15 @@ B200SPMV_EXPORT int    b200spmv_csr_short_mv(void* stream, int dtype, int64_t ro
                                              int32_t base, const void* alpha, const void* beta, int scalars_on_device,
                                              const void* x, void* y);
 
+/* The same product with a dot product in its epilogue: *dot_out = y . w, fp64 accumulation, deterministic (SURVEY.md 8(f)-2:
+ * T = A*P and T . P of cg_example.c:220-227 in one pass).  dot_out: device memory.  workspace:
+ * b200spmv_csr_short_dot_workspace_bytes() bytes, zeroed once before its first use. */
+B200SPMV_EXPORT size_t b200spmv_csr_short_dot_workspace_bytes(void);
+B200SPMV_EXPORT int    b200spmv_csr_short_mv_dot(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz,
+                                                 const void* row_offsets, const void* col_ind, const void* values,
+                                                 int32_t base, const void* alpha, const void* beta, int scalars_on_device,
+                                                 const void* x, void* y, const void* w, double* dot_out, void* workspace);
+
 /* CSR, opA = TRANSPOSE (spmv_csr_transpose.cu): y[cols] = alpha * A^T * x[rows] + beta * y; no plan, no workspace; one
  * fp atomic per non-zero, so the summation order (not the tolerance) differs between runs. */
 B200SPMV_EXPORT int    b200spmv_csr_transpose_mv(void* stream, int dtype, int64_t rows, int64_t cols, int64_t nnz,

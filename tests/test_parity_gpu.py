@@ -833,3 +833,37 @@ def test_transposed_spmv_is_native(cs, b200, closed, fmt, dtype):
     torch.cuda.synchronize()
     op.close()
     assert relerr(y.cpu().numpy(), A.T @ x.astype(np.float64)) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_short_kernel_with_the_dot_product_in_its_epilogue(b200, dtype):
+    """b200spmv_csr_short_mv_dot: T = A*P and T . P of a CG iteration (cg_example.c:220-227) in one launch; the dot is
+    accumulated in fp64, deterministic, and the arrival counter of its workspace is left at zero (second call = same bits)."""
+    import ctypes as C
+    L = b200.lib
+    L.b200spmv_csr_short_dot_workspace_bytes.restype = C.c_size_t
+    off, col, val = O.gen_stencil5(257)
+    n = 257 * 257
+    val = val.astype(NP[dtype])
+    x = O.uniform(5, n).astype(NP[dtype])
+    want_y = O.spmv_csr(off, col, val, x, np.zeros(n, NP[dtype]), 1.0, 0.0)
+    want_dot = float(np.dot(want_y.astype(np.float64), x.astype(np.float64)))
+    d_off, d_col, d_val, d_x = dev(off), dev(col), dev(val), dev(x)
+    y = torch.full((n,), float("nan"), dtype=dtype, device="cuda")
+    out = torch.zeros(2, dtype=torch.float64, device="cuda")
+    ws = torch.zeros(int(L.b200spmv_csr_short_dot_workspace_bytes()), dtype=torch.uint8, device="cuda")
+    ct = C.c_double if dtype == torch.float64 else C.c_float
+    one, zero = ct(1.0), ct(0.0)
+    got = []
+    for k in range(2):
+        rc = L.b200spmv_csr_short_mv_dot(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_int(1 if dtype == torch.float64 else 0),
+                                         C.c_int64(n), C.c_int64(n), C.c_int64(int(col.size)), C.c_void_p(d_off.data_ptr()),
+                                         C.c_void_p(d_col.data_ptr()), C.c_void_p(d_val.data_ptr()), C.c_int32(0), C.byref(one), C.byref(zero),
+                                         C.c_int(0), C.c_void_p(d_x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_void_p(d_x.data_ptr()),
+                                         C.c_void_p(out[k:k + 1].data_ptr()), C.c_void_p(ws.data_ptr()))
+        assert rc == 0
+        torch.cuda.synchronize()
+        got.append(float(out[k].item()))
+    assert relerr(y.cpu().numpy(), want_y) < TOL[dtype]
+    assert abs(got[0] - want_dot) <= (1e-12 if dtype == torch.float64 else 1e-5) * abs(want_dot)
+    assert got[0] == got[1]
