@@ -398,6 +398,34 @@ def other_configs_leg(torch, cs, W, api, peak):
     return out
 
 
+def spmm_sharded_leg(torch, dist, cs, W, api, rank, world):
+    """BASELINE.json configs[4] as it is quoted (8 x B200): A (2M x 2M, 32 per row, fp32) and C in contiguous row blocks, B (2M x 64,
+    column-major) replicated on every GPU -- the product shards with no exchange step at all; time = max over ranks."""
+    rows_g, per_row, nn = 2_000_000, 32, 64
+    rows = rows_g // world
+    g = torch.Generator(device="cuda").manual_seed(5 + rank)       # this rank's row block (uniformly random columns: any block looks alike)
+    col = torch.randint(0, rows_g, (rows, per_row), device="cuda", generator=g, dtype=torch.int32).sort(dim=1).values.reshape(-1).contiguous()
+    off = (torch.arange(rows + 1, device="cuda", dtype=torch.int64) * per_row).to(torch.int32)
+    val = W.uniform(43 + rank, rows * per_row, torch.float32)
+    B = W.uniform(46, rows_g * nn, torch.float32)
+    C0 = torch.zeros(rows * nn, dtype=torch.float32, device="cuda")
+    ts = []
+    for _ in range(4):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cs.spmm(api, rows, rows_g, dict(off=off, col=col, val=val), B, C0, 1.0, 0.0, timing=(e0, e1))
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ts.append(float(t.item()) * 1e3)
+    us = sorted(ts[1:])[1]
+    flops = 2 * rows_g * per_row * nn
+    return {"config5_spmm_f32_2m_n64": {"workload": f"fp32 CSR x dense, A 2M x 2M with 32 per row in {world} row blocks, B 2M x 64 column-major replicated, "
+                                                    "C in row blocks; no exchange step", "us_per_spmm": round(us, 1), "gflops": round(flops / us / 1e3, 1),
+                                        "n_gpus": world, "scaling": "strong"}}
+
+
 def cg_leg(torch, dist, cs, W, api, rank, world):
     """BASELINE.json configs[3]: CG, fp64, 5-pt Poisson 8192^2 (cg_example.c:71-128 generator), 200 fixed iterations,
     row-sharded over the N GPUs (strong scaling), iterations/s = 200 / max-over-ranks device time."""
@@ -695,6 +723,12 @@ def run_ours(args):
         except Exception as e:  # pragma: no cover
             cg = {"error": repr(e)}
     others = None
+    if dist_on and not args.no_extra and 2_000_000 % world == 0:
+        torch.cuda.empty_cache()
+        try:
+            others = spmm_sharded_leg(torch, dist, cs, W, api, rank, world)
+        except Exception as e:  # pragma: no cover
+            others = {"error": repr(e)}
     if not dist_on and not args.no_extra:
         torch.cuda.empty_cache()
         try:
