@@ -16,12 +16,13 @@
 //     rate drops from 1.26 to 0.95 elements/clk/SM when 100 KB of it is carved out, scripts/micro_gather.cu), a step of 32
 //     non-zeros inside one row costs one add; a step with row ends costs one butterfly + a segmented shuffle scan with as
 //     many levels as its longest remaining segment; the end lanes look their rows up in nzrow and store y.  Rows crossing
-//     a warp chunk are stitched per CTA (the last warp to finish, fixed order), rows crossing a CTA (1024 non-zeros) by the
-//     small csr_flat_fixup_kernel launch that follows (one thread per CTA border): bit-reproducible, no atomics.  The EMPTY
-//     rows (y = beta*y) are scaled by extra CTAs at the end of the main kernel's grid, which run while the last chunks drain.
-//     (Round 2 also tried finishing the CTA-crossing rows inside the kernel -- ticketed CTA indices + decoupled look-back,
-//     single launch: 138 us instead of 84 us on R-MAT 1M, profiles/sweep_r2_flat_lookback_vs_fixup.txt -- and scaling the
-//     empty rows from the chunk that ends the row in front of them: 92 us.)
+//     a warp chunk are stitched per CTA (the last warp to finish, fixed order), rows crossing a CTA (1024 non-zeros) and the
+//     EMPTY rows (y = beta*y) by the small csr_flat_fixup_kernel launch that follows: bit-reproducible, no atomics.
+//     Round 2 measured three alternatives to that second launch, all rejected (profiles/sweep_r2_flat_*.txt): finishing the
+//     CTA-crossing rows inside the kernel (ticketed CTA indices + decoupled look-back, single launch): 138 us instead of
+//     84 us on R-MAT 1M; scaling the empty rows from the chunk that ends the row in front of them: 92 us; scaling them by
+//     extra CTAs at the end of the main grid: 84.9 us on 1M, 832 instead of 814 us on 10M.  A per-chunk ballot that spares
+//     the steps without a row end their one shuffle changed nothing measurable either.
 //
 // Replaces cusparse::csrmv_v3_kernel behind cusparseSpMV for preprocessed CSR descriptors (call sites:
 // cuSPARSE/spmv_csr/spmv_csr_example.c:104-112, cuSOLVERSp2cuDSS/csreigvsi2cuDSS_double.cpp:148-150,221).
@@ -46,12 +47,6 @@ namespace b200 {
 #ifndef B200_FLAT_NZPRE      // 1: the chunk's first 32 nzrow entries are loaded with the stream and looked up by shuffle
 #define B200_FLAT_NZPRE 0    //    (measured r2f: 85.2 us with, 84.1 us without -- the look-up load already hides behind the shuffles)
 #endif
-#ifndef B200_FLAT_QUIET_BALLOT   // 1: one ballot per chunk tells which steps end no row; those steps then need no shuffle at all
-#define B200_FLAT_QUIET_BALLOT 1
-#endif
-#ifndef B200_FLAT_EMPTY_TAIL     // 1: the empty rows (y = beta*y) are scaled by extra CTAs at the END of the main kernel's grid, which run
-#define B200_FLAT_EMPTY_TAIL 1   //    while the last non-zero chunks drain; 0: by the fix-up launch (one thread per row)
-#endif
 constexpr int PLAN_STEPS = 8;                      // the plan's granularity: chunk_run has one entry per 8 steps = 256 non-zeros
 constexpr int PLAN_CHUNK = 32 * PLAN_STEPS;
 constexpr int FLAT_STEPS = B200_FLAT_STEPS;        // 32-element steps per warp chunk (8, 16 or 32)
@@ -68,8 +63,6 @@ constexpr int FLAT_PAD_NNZ = 2048;                 // the plan arrays are padded
 static_assert(FLAT_PAD_NNZ % FLAT_CTA_NNZ == 0, "FLAT_WARPS x FLAT_STEPS must divide 64");
 constexpr int FLAT_BATCH = B200_FLAT_BATCH;
 constexpr int SCAN_ITEMS = 2048;                   // items per block of the preprocessing scans
-constexpr int EMPTY_ROWS_PER_THREAD = 16;          // empty-row CTAs: FLAT_BLOCK threads x 16 rows each, coalesced
-constexpr int EMPTY_ROWS_PER_CTA = FLAT_BLOCK * EMPTY_ROWS_PER_THREAD;
 static_assert(FLAT_STEPS % FLAT_BATCH == 0, "steps per chunk must be a multiple of the batch");
 
 struct FlatPlan {
@@ -251,7 +244,6 @@ struct FlatArgs {
     int        base;
     int        rows;
     int        nnz;
-    int        nctas;      // CTAs that own non-zeros; CTAs behind them (B200_FLAT_EMPTY_TAIL) scale the empty rows
     Scalars<T> s;
     FlatPlan   plan;
 };
@@ -276,23 +268,6 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
     __shared__ T   sFirst[FLAT_WARPS], sLast[FLAT_WARPS];
     __shared__ int sFrow[FLAT_WARPS];                      // >= 0: row of the chunk's first row end (deferred to the stitch)
     __shared__ int sArrived;                               // warps that have deposited their partials
-#if B200_FLAT_EMPTY_TAIL
-    if ((int)blockIdx.x >= a.nctas) {
-        // EMPTY rows never show up in the non-zero stream.  These CTAs are dispatched last and run next to the draining
-        // chunk CTAs: y = beta * y for every row with off[r] == off[r + 1].  (beta == 1: the launch adds no such CTAs
-        // when beta is known on the host; with a device-side beta they find nothing to do.)
-        const T beta = a.s.b();
-        if (beta == T(1)) return;
-        const T alpha = a.s.a();
-        const long long r0 = (long long)((int)blockIdx.x - a.nctas) * EMPTY_ROWS_PER_CTA + threadIdx.x;
-#pragma unroll 4
-        for (int k = 0; k < EMPTY_ROWS_PER_THREAD; k++) {
-            const long long r = r0 + (long long)k * FLAT_BLOCK;
-            if (r < a.rows && __ldg(a.off + r) == __ldg(a.off + r + 1)) flat_store_y(a.y + r, alpha, T(0), beta);
-        }
-        return;
-    }
-#endif
     if (threadIdx.x == 0) sArrived = 0;
     __syncthreads();                                       // the only CTA-wide barrier, before any work: nobody waits at the end
 
@@ -307,9 +282,6 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
     if (active) {
         const int n0 = (int)c0, n1 = min(n0 + FLAT_CHUNK, a.nnz);
         const unsigned mreg = lane < FLAT_STEPS ? __ldg(a.plan.endmask + c * FLAT_STEPS + lane) : 0u;
-#if B200_FLAT_QUIET_BALLOT
-        const unsigned quiet = __ballot_sync(0xffffffffu, mreg == 0u);       // bit k: no row ends in step k
-#endif
         int run = __ldg(a.plan.chunk_run + c * (FLAT_STEPS / PLAN_STEPS));   // rows that ended before this chunk
 #if B200_FLAT_NZPRE
         const int run0 = run;
@@ -346,14 +318,9 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
             if (kb + FLAT_BATCH < FLAT_STEPS && n0 + (kb + FLAT_BATCH) * 32 < n1) issue(kb + FLAT_BATCH);
 #pragma unroll
             for (int k = 0; k < FLAT_BATCH; k++) {
+                const unsigned m = __shfl_sync(0xffffffffu, mreg, kb + k);
                 const T pk = p[k];
-#if B200_FLAT_QUIET_BALLOT
-                if ((quiet >> (kb + k)) & 1u) { acc += pk; continue; }      // the whole step lies inside one row: no shuffle
-                const unsigned m = __shfl_sync(0xffffffffu, mreg, kb + k);
-#else
-                const unsigned m = __shfl_sync(0xffffffffu, mreg, kb + k);
                 if (m == 0u) { acc += pk; continue; }      // the whole step lies inside one row
-#endif
                 const int e1 = __ffs(m) - 1, ek = 31 - __clz(m);
                 // my row (if I end one): issued first, the look-up's latency hides behind the shuffles below
                 const bool is_end = (m >> lane) & 1u;
@@ -436,11 +403,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) csr_flat_fixup_kernel(const FlatArgs<T> a, long long nctas) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const T alpha = a.s.a(), beta = a.s.b();
-#if !B200_FLAT_EMPTY_TAIL
     if (t < a.rows && beta != T(1)) {                       // beta == 1 (a later column panel of a sharded product): y stays as it is
         if (__ldg(a.off + t) == __ldg(a.off + t + 1)) flat_store_y(a.y + t, alpha, T(0), beta);
     }
-#endif
     if (t >= nctas - 1) return;
     const bool tail_open = !(__ldg(a.plan.endmask + (t + 1) * FLAT_CTA_WORDS - 1) >> 31);
     if (!tail_open) return;
@@ -479,22 +444,12 @@ static int launch_flat(cudaStream_t stream, int64_t rows, int64_t nnz, const voi
         return (int)cudaGetLastError();
     }
     const int64_t nctas = flat_num_ctas(nnz);
-    a.nctas = (int)nctas;
-    // with a host-side beta == 1 the empty rows need no pass at all
-    const bool skip_rows = !on_device && *(const T*)beta == T(1);
-#if B200_FLAT_EMPTY_TAIL
-    const int64_t empty_ctas = skip_rows ? 0 : (rows + EMPTY_ROWS_PER_CTA - 1) / EMPTY_ROWS_PER_CTA;
-    csr_flat_kernel<T><<<(unsigned)(nctas + empty_ctas), FLAT_BLOCK, 0, stream>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    if (nctas < 2) return 0;                                // one CTA: no row crosses a CTA border
-    const int64_t work = nctas - 1;
-#else
     csr_flat_kernel<T><<<(unsigned)nctas, FLAT_BLOCK, 0, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
+    // empty rows + CTA-crossing rows; with a host-side beta == 1 the empty rows need no pass at all
+    const bool skip_rows = !on_device && *(const T*)beta == T(1);
     const int64_t work = (!skip_rows && rows > nctas - 1) ? rows : (nctas - 1 > 0 ? nctas - 1 : 1);
-#endif
     csr_flat_fixup_kernel<T><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(a, (long long)nctas);
     return (int)cudaGetLastError();
 }
