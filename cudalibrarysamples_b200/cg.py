@@ -119,13 +119,13 @@ class FusedCgSolver:
             self.sh.spmv(p, t, alpha=1.0, beta=0.0)                          # T = A * P      (cg_example.c:220-224)
             self._dot(t, p, s[2:3])                                          # denom = T . P  (:227)
         nxt = 1 - cur
-        self._check(self.L.b200cg_update_xr(self._stream(), C.c_int64(self.n), self._p(x), self._p(r), self._p(p), self._p(t),
-                                            self._p(s[cur:cur + 1]), self._p(s[2:3]), self._p(s[nxt:nxt + 1]), self._p(self.ws)),
-                    "b200cg_update_xr")                                      # X += aP, R -= aT, delta' = R.R (:232-247)
+        # 8 vector passes: R -= aT with delta' = R.R, then X += aP and P = R + (delta'/delta) P in one pass (P read once)
+        self._check(self.L.b200cg_update_r(self._stream(), C.c_int64(self.n), self._p(r), self._p(t), self._p(s[cur:cur + 1]), self._p(s[2:3]),
+                                           self._p(s[nxt:nxt + 1]), self._p(self.ws)), "b200cg_update_r")       # (:241-247)
         if self.sh.world > 1:
             dist.all_reduce(s[nxt:nxt + 1], group=self.sh.group)
-        self._check(self.L.b200cg_update_p(self._stream(), C.c_int64(self.n), self._p(p), self._p(r), self._p(s[nxt:nxt + 1]),
-                                           self._p(s[cur:cur + 1])), "b200cg_update_p")   # P = R + (delta'/delta) P (:280-286)
+        self._check(self.L.b200cg_update_xp(self._stream(), C.c_int64(self.n), self._p(x), self._p(p), self._p(r), self._p(s[cur:cur + 1]),
+                                            self._p(s[2:3]), self._p(s[nxt:nxt + 1])), "b200cg_update_xp")       # (:236-239, :280-286)
 
     def run(self, iters: int):
         x = torch.zeros_like(self.b)
@@ -183,7 +183,7 @@ class FusedCgSolver:
         spmv = ("T = A*P and T.P in one csr_short_kernel launch (b200spmv_csr_short_mv_dot)" if self.fuse_dot
                 else "SpMV through the C ABI + b200cg_dot")
         return ("CG (cg_example.c:215-287 without the IC(0) preconditioner): " + spmv + " + fused sm_100a BLAS-1 kernels "
-                "(b200cg_update_xr = 2 axpy + nrm2 in one pass, b200cg_update_p), all scalars on the device, "
+                "(b200cg_update_r = axpy + nrm2 in one pass, b200cg_update_xp = x and p updates in one pass: 8 vector passes per iteration), all scalars on the device, "
                 + how + (f" (graph capture failed: {self.graph_error})" if self.graph_error else ""))
 
 

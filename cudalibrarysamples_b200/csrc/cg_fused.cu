@@ -7,6 +7,8 @@
 //     cublasDnrm2(R) -> host            (:247)      /
 //     beta = delta_new / delta on host  (:280)      \
 //     cublasDscal + cublasDaxpy on P    (:281-286)  /   b200cg_update_p    one pass: p = r + beta * p
+// ... or, one vector pass cheaper (8 instead of 9 per iteration: p is read once, next to its own update):
+//     b200cg_update_r   r -= alpha t, r.r in the same pass        b200cg_update_xp   x += alpha p_old;  p = r + beta p_old
 // No host synchronisation anywhere: scalars are read from / written to device memory, so the whole iteration can be
 // captured in a CUDA graph (cuSPARSE/graph_capture/graph_capture_example.c:118-135 shows the pattern for SpVV).
 // Reductions are two-level and deterministic: every CTA deposits one partial, the CTA that arrives last adds them in CTA
@@ -112,6 +114,53 @@ __global__ void __launch_bounds__(BLOCK) update_p_kernel(int64_t n, double* __re
     }
 }
 
+// --- the same iteration in 8 instead of 9 vector passes: the x update moves next to the p update (p is read once) ---
+// alpha = delta / denom;  r -= alpha t;  delta_new = r . r          (reads t, r; writes r)
+__global__ void __launch_bounds__(BLOCK) update_r_kernel(int64_t n, double* __restrict__ r, const double* __restrict__ t,
+                                                         const double* __restrict__ delta, const double* __restrict__ denom,
+                                                         double* __restrict__ delta_new, double* __restrict__ ws) {
+    __shared__ double sred[BLOCK / 32];
+    const double alpha = *delta / *denom;
+    double s = 0;
+    const int64_t stride = (int64_t)gridDim.x * BLOCK * 2;
+    for (int64_t i = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) * 2; i < n; i += stride) {
+        if (i + 1 < n) {
+            const double2 tt = *reinterpret_cast<const double2*>(t + i);
+            double2 rr = *reinterpret_cast<double2*>(r + i);
+            rr.x -= alpha * tt.x; rr.y -= alpha * tt.y;
+            *reinterpret_cast<double2*>(r + i) = rr;
+            s += rr.x * rr.x + rr.y * rr.y;
+        } else {
+            const double rn = r[i] - alpha * t[i];
+            r[i] = rn;
+            s += rn * rn;
+        }
+    }
+    const double tt = block_sum(s, sred);
+    if (threadIdx.x == 0) grid_sum_finish(tt, ws, delta_new);
+}
+
+// alpha = delta / denom;  x += alpha p;  beta = delta_new / delta;  p = r + beta p          (reads x, p, r; writes x, p)
+__global__ void __launch_bounds__(BLOCK) update_xp_kernel(int64_t n, double* __restrict__ x, double* __restrict__ p,
+                                                          const double* __restrict__ r, const double* __restrict__ delta,
+                                                          const double* __restrict__ denom, const double* __restrict__ delta_new) {
+    const double alpha = *delta / *denom, beta = *delta_new / *delta;
+    const int64_t stride = (int64_t)gridDim.x * BLOCK * 2;
+    for (int64_t i = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) * 2; i < n; i += stride) {
+        if (i + 1 < n) {
+            const double2 rr = *reinterpret_cast<const double2*>(r + i);
+            double2 pp = *reinterpret_cast<double2*>(p + i), xx = *reinterpret_cast<double2*>(x + i);
+            xx.x += alpha * pp.x; xx.y += alpha * pp.y;
+            pp.x = rr.x + beta * pp.x; pp.y = rr.y + beta * pp.y;
+            *reinterpret_cast<double2*>(x + i) = xx;
+            *reinterpret_cast<double2*>(p + i) = pp;
+        } else {
+            x[i] += alpha * p[i];
+            p[i] = r[i] + beta * p[i];
+        }
+    }
+}
+
 static int grid_for(int64_t n) {
     int64_t g = (n / 2 + BLOCK - 1) / BLOCK;
     if (g > MAX_CTAS) g = MAX_CTAS;
@@ -140,6 +189,21 @@ int b200cg_update_xr(void* stream, int64_t n, double* x, double* r, const double
     if (n < 0 || !delta || !denom || !delta_new || !workspace || (n > 0 && (!x || !r || !p || !t))) return -1;
     if (!aligned16(x) || !aligned16(r) || !aligned16(p) || !aligned16(t)) return -1;
     update_xr_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, x, r, p, t, delta, denom, delta_new, (double*)workspace);
+    return (int)cudaGetLastError();
+}
+
+int b200cg_update_r(void* stream, int64_t n, double* r, const double* t, const double* delta, const double* denom, double* delta_new,
+                    void* workspace) {
+    if (n < 0 || !delta || !denom || !delta_new || !workspace || (n > 0 && (!r || !t)) || !aligned16(r) || !aligned16(t)) return -1;
+    update_r_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, r, t, delta, denom, delta_new, (double*)workspace);
+    return (int)cudaGetLastError();
+}
+
+int b200cg_update_xp(void* stream, int64_t n, double* x, double* p, const double* r, const double* delta, const double* denom,
+                     const double* delta_new) {
+    if (n < 0 || !delta || !denom || !delta_new || (n > 0 && (!x || !p || !r))) return -1;
+    if (!aligned16(x) || !aligned16(p) || !aligned16(r)) return -1;
+    update_xp_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, x, p, r, delta, denom, delta_new);
     return (int)cudaGetLastError();
 }
 
