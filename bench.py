@@ -41,8 +41,8 @@ UNIT = "GB/s"
 ROWS_PER_GPU = 1_000_000
 AVG_NNZ = 16
 CG_GRID = 8192
-ROW_WEIGHT = 12.0      # N>1: work of a row block = nnz + ROW_WEIGHT * rows (measured at N = 2: local products 104 / 165 us at weight 0,
-                       #      121 / 128 us at 8, 131 / 117 us at 16)
+ROW_WEIGHT = 8.0       # N>1: work of a row block = nnz + ROW_WEIGHT * rows.  Fitted on the N = 2 run of round 2 (csr_flat_kernel, weight 12:
+                       #      20.9 M nnz / 0.59 M rows in 105.7 us, 11.1 M nnz / 1.41 M rows in 92.2 us -> 4.1 us per M nnz + 33 us per M rows)
 CG_ITERS = 200
 
 

@@ -103,6 +103,10 @@ if os.environ.get("SWEEP_SET") == "flat":
 if os.environ.get("SWEEP_SET") == "flat3":
     # csr_flat_kernel: (quiet-step ballot, empty rows scaled by tail CTAs of the main grid)
     VARIANTS = {f"flat3_qb{qb}_et{et}": dict(FLAT3=(qb, et)) for (qb, et) in [(1, 1), (0, 1), (1, 0), (0, 0)]}
+if os.environ.get("SWEEP_SET") == "flat4":
+    # csr_flat_kernel: deeper load batches / more resident CTAs (the fp32 kernel has registers to spare)
+    VARIANTS = {f"flat4_occ{o}_k{k}_w{w}_s{st}": dict(FLAT=(o, k, w, st)) for (o, k, w, st) in
+                [(10, 8, 4, 8), (12, 8, 4, 8), (12, 4, 4, 8), (8, 8, 4, 8)]}
 if os.environ.get("SWEEP_SET") == "short":
     # csr_short_kernel: (warps per CTA, load steps per pass, resident CTAs)
     VARIANTS = {f"short_w{w}_s{st}_occ{o}": dict(SHORT=(w, st, o)) for (w, st, o) in
