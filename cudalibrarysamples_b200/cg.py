@@ -90,8 +90,10 @@ class FusedCgSolver:
         self.scal = torch.zeros(8, dtype=torch.float64, device=dev)        # [0], [1]: delta of even / odd iterations, [2]: t.p
         self.use_graph = (sh.world == 1 and os.environ.get("B200CG_GRAPH", "1") != "0") if use_graph is None else use_graph
         self.graph_error = None
-        # T = A*P and T . P in one kernel where the local matrix allows it (all rows short: csr_short_kernel's DOT variant)
-        self.fuse_dot = os.environ.get("B200CG_FUSE_DOT", "1") != "0" and hasattr(sh, "can_fuse_dot") and sh.can_fuse_dot()
+        # T = A*P and T . P in one kernel where the local matrix allows it (all rows short: csr_short_kernel's DOT variant).
+        # Opt-in: measured on 5-pt 8192^2 (profiles/launches_r2_cg_iteration.csv) the DOT variant costs 1278 us against
+        # 1068 + 158 us for the plain kernel + b200cg_dot -- the extra live registers spill in the 48-register kernel.
+        self.fuse_dot = os.environ.get("B200CG_FUSE_DOT", "0") == "1" and hasattr(sh, "can_fuse_dot") and sh.can_fuse_dot()
 
     def _stream(self):
         return self.C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -35,8 +35,8 @@ namespace b200 {
 #ifndef B200_FLAT_MIN_CTAS
 #define B200_FLAT_MIN_CTAS 10     // x 128 threads, 48 registers (sweep r2e: 84.1 us on R-MAT 1M; 8 x 256 threads at 56 registers: 90.4 us)
 #endif
-#ifndef B200_FLAT_BATCH
-#define B200_FLAT_BATCH 4
+#ifndef B200_FLAT_BATCH        // steps whose col / val loads are all issued before the first gather -- fp64; the fp32 kernel has the
+#define B200_FLAT_BATCH 4      // registers for all 8 steps of a chunk (sweep r2k on R-MAT 1M: fp32 72.0 -> 69.5 us at 8, fp64 84.2 -> 86.3)
 #endif
 #ifndef B200_FLAT_STEPS
 #define B200_FLAT_STEPS 8
@@ -61,9 +61,14 @@ constexpr int FLAT_CTA_NNZ = FLAT_CHUNK * FLAT_WARPS;   // 2048 non-zeros per CT
 constexpr int FLAT_CTA_WORDS = FLAT_CTA_NNZ / 32;
 constexpr int FLAT_PAD_NNZ = 2048;                 // the plan arrays are padded to this many non-zeros (independent of FLAT_WARPS)
 static_assert(FLAT_PAD_NNZ % FLAT_CTA_NNZ == 0, "FLAT_WARPS x FLAT_STEPS must divide 64");
-constexpr int FLAT_BATCH = B200_FLAT_BATCH;
+constexpr int FLAT_BATCH64 = B200_FLAT_BATCH;
+#ifdef B200_FLAT_BATCH32
+constexpr int FLAT_BATCH32 = B200_FLAT_BATCH32;
+#else
+constexpr int FLAT_BATCH32 = (2 * B200_FLAT_BATCH <= B200_FLAT_STEPS) ? 2 * B200_FLAT_BATCH : B200_FLAT_BATCH;
+#endif
 constexpr int SCAN_ITEMS = 2048;                   // items per block of the preprocessing scans
-static_assert(FLAT_STEPS % FLAT_BATCH == 0, "steps per chunk must be a multiple of the batch");
+static_assert(FLAT_STEPS % FLAT_BATCH64 == 0 && FLAT_STEPS % FLAT_BATCH32 == 0, "steps per chunk must be a multiple of the batch");
 
 struct FlatPlan {
     unsigned* endmask;    // [nctas * 64]   zero-padded behind nnz
@@ -290,6 +295,7 @@ __global__ void __launch_bounds__(FLAT_BLOCK, B200_FLAT_MIN_CTAS) csr_flat_kerne
         const int* colp = a.col + n0;
         const T*   valp = a.val + n0;
         const T*   xp = a.x - a.base;
+        constexpr int FLAT_BATCH = sizeof(T) == 8 ? FLAT_BATCH64 : FLAT_BATCH32;
         int cc[FLAT_BATCH];
         T   vv[FLAT_BATCH];
         auto issue = [&](int kb) {

@@ -501,8 +501,9 @@ def test_sell_ragged_rmat(cs, b200):
 
 
 # ------------------------------------------------------------------------------------------ fused CG step (8(f)-2)
+@pytest.mark.parametrize("fuse_dot", [False, True])
 @pytest.mark.parametrize("graph", [False, True])
-def test_fused_cg_matches_the_sample_loop(cs, b200, graph):
+def test_fused_cg_matches_the_sample_loop(cs, b200, graph, fuse_dot):
     """The fused device-scalar CG driver (csrc/cg_fused.cu) against a plain numpy restatement of cg_example.c:215-287
     (no preconditioner) on the sample's own matrix family; with and without CUDA-graph replay."""
     from cudalibrarysamples_b200.cg import CgSolver, FusedCgSolver
@@ -526,6 +527,8 @@ def test_fused_cg_matches_the_sample_loop(cs, b200, graph):
         return cs.SpMVOperator(b200, "csr", rr, cc, arrays, preprocess=True)
     sh = ShardedCsr(dev(off), dev(col), dev(val), 0, 1, make_local, balance="rows")
     solver = FusedCgSolver(sh, dev(b), use_graph=graph)
+    solver.fuse_dot = fuse_dot and sh.can_fuse_dot()          # T = A*P with T.P in its epilogue (opt-in: B200CG_FUSE_DOT=1)
+    assert solver.fuse_dot == fuse_dot
     xs, norms = solver.run(iters)
     torch.cuda.synchronize()
     assert solver.graph_error is None, solver.graph_error
