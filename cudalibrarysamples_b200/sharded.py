@@ -233,6 +233,9 @@ class ShardedCsr:
         # Two copy streams, blocks issued IN ARRIVAL ORDER alternately on them: measured at N = 2 one copy-engine peer copy of
         # 8 MB runs at ~340 GB/s and splitting it over more streams does not help, so two copies in flight fill most of the
         # 900 GB/s NVLink ingress while the early blocks still land early (the panel pipeline below feeds on that).
+        # B200SPMV_XCHG_SM_CTAS=n (> 0): pull the peer shards with an SM copy kernel of n CTAs (csrc/peer_sync.cu: LDG.128 from
+        # peer memory over NVLink) instead of copy-engine copies
+        self.sm_pull_ctas = int(os.environ.get("B200SPMV_XCHG_SM_CTAS", "0"))
         self.copy_streams = [torch.cuda.Stream() for _ in range(2)]
         self.own_stream = torch.cuda.Stream()
         self.ev_ready, self.ev_own = torch.cuda.Event(), torch.cuda.Event()
@@ -243,8 +246,9 @@ class ShardedCsr:
             return "none (single GPU)"
         if self.exchange == "halo":
             return f"halo exchange: {self.exchanged_elements * self.val.element_size()} B per step over all ranks (batch_isend_irecv)"
-        how = {"p2p": "x shards in symmetric memory; one device-side barrier, then copy-engine peer copies over NVLink on side streams "
-                      "(double-buffered shards)",
+        how = {"p2p": "x shards in symmetric memory; one device-side barrier, then "
+                      + (f"SM pull kernels ({self.sm_pull_ctas} CTAs, LDG.128 from peer memory)" if getattr(self, "sm_pull_ctas", 0) > 0 else "copy-engine peer copies")
+                      + " over NVLink on side streams (double-buffered shards)",
                "allgather": "one NCCL all_gather_into_tensor on a side stream"}[self.exchange]
         if getattr(self, "_graphs", None):
             how += "; the whole step replayed as a CUDA graph"
@@ -303,7 +307,15 @@ class ShardedCsr:
             for k, h in enumerate(self.pull_order):               # peer blocks in arrival order, alternating over two streams
                 st = self.copy_streams[k & 1]
                 with torch.cuda.stream(st):
-                    self.x_full[h * blk:(h + 1) * blk].copy_(self.peer[i][h], non_blocking=True)
+                    if self.sm_pull_ctas > 0:
+                        esz = self.x_full.element_size()
+                        rc = self._L.b200peer_pull(self._C.c_void_p(st.cuda_stream), self._C.c_void_p(self.x_full.data_ptr() + h * blk * esz),
+                                                   self._C.c_void_p(self.peer[i][h].data_ptr()), self._C.c_size_t(blk * esz),
+                                                   self._C.c_int(self.sm_pull_ctas))
+                        if rc != 0:
+                            raise RuntimeError(f"b200peer_pull failed with code {rc}")
+                    else:
+                        self.x_full[h * blk:(h + 1) * blk].copy_(self.peer[i][h], non_blocking=True)
                     self.ev_block[k].record(st)
             return self._p2p_waits(main)
         if self.exchange == "allgather" and hasattr(self, "side"):
