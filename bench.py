@@ -41,8 +41,9 @@ UNIT = "GB/s"
 ROWS_PER_GPU = 1_000_000
 AVG_NNZ = 16
 CG_GRID = 8192
-ROW_WEIGHT = 8.0       # N>1: work of a row block = nnz + ROW_WEIGHT * rows.  Fitted on the N = 2 run of round 2 (csr_flat_kernel, weight 12:
-                       #      20.9 M nnz / 0.59 M rows in 105.7 us, 11.1 M nnz / 1.41 M rows in 92.2 us -> 4.1 us per M nnz + 33 us per M rows)
+ROW_WEIGHT = 2.0       # N>1: work of a row block = nnz + ROW_WEIGHT * rows.  Fitted on the N = 2 runs of round 2 (csr_flat_kernel; weight 8:
+                       #      19.7 M nnz / 0.54 M rows in 100.4 us, 12.3 M nnz / 1.46 M rows in 74.5 us -> ~5.1 us per M nnz + ~8 us per M rows;
+                       #      round 1's tile kernels paid far more per row: 12)
 CG_ITERS = 200
 
 
@@ -607,7 +608,8 @@ def run_ours(args):
         local["rows_per_rank"] = [int(b - a) for a, b in zip(sh.bounds.tolist()[:-1], sh.bounds.tolist()[1:])]
         if sh.panels:
             def xonly():
-                sh._start_exchange(xs)()
+                for w in sh._start_exchange(xs):       # one wait per panel
+                    w()
             for _ in range(3):
                 xonly()
             ms_x, _, _ = time_steps(torch, xonly, args.steps, True)
