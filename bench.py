@@ -607,13 +607,19 @@ def run_ours(args):
         local["local_product_us_per_rank"] = [round(float(t.item()), 2) for t in allk]
         local["rows_per_rank"] = [int(b - a) for a, b in zip(sh.bounds.tolist()[:-1], sh.bounds.tolist()[1:])]
         if sh.panels:
-            def xonly():
-                for w in sh._start_exchange(xs):       # one wait per panel
-                    w()
-            for _ in range(3):
-                xonly()
-            ms_x, _, _ = time_steps(torch, xonly, args.steps, True)
-            local["exchange_alone_us"] = round(ms_x / args.steps * 1e3, 2)
+            # a diagnostic, not the metric: a host-side error in it (the same on every rank: the code path is rank-symmetric)
+            # must not cost the run its JSON line
+            try:
+                def xonly():
+                    for w in sh._start_exchange(xs):       # one wait per panel
+                        w()
+                for _ in range(3):
+                    xonly()
+                ms_x, _, _ = time_steps(torch, xonly, args.steps, True)
+                local["exchange_alone_us"] = round(ms_x / args.steps * 1e3, 2)
+            except (TypeError, AttributeError, ValueError, KeyError, IndexError) as e:  # pragma: no cover
+                local["exchange_alone_us"] = None
+                local["exchange_alone_error"] = repr(e)
         kern_ms = max(float(t.item()) for t in allk) * 1e-3
     else:
         kern_ms = ms_step

@@ -67,6 +67,15 @@ def _worker(rank, world, port, rows, q):
         zs = sh.new_y_shard()
         sh.spmv(sh.new_x_shard(y_full), zs, alpha=1.0, beta=0.0)
         gathered = sh.x_full[:sh.global_rows].clone()
+        # the timing-loop form bench.py uses (make_step: fixed buffers, alpha = 1, beta = 0, one call per column panel)
+        zs2 = sh.new_y_shard(torch.from_numpy(O.uniform(7, rows)))        # beta = 0: whatever y held is overwritten
+        step = sh.make_step(sh.new_x_shard(y_full), zs2, graph=False)
+        step()
+        step()
+        assert len(sh.panel_calls) == len(sh.panel_groups) == min(world - 1, 3) + 1
+        assert sorted(b for g in sh.panel_groups for b in g) == list(range(world))   # every x block in exactly one panel
+        assert sh.panel_groups[0] == [rank] and [b for g in sh.panel_groups[1:] for b in g] == sh.pull_order
+        assert torch.equal(zs2, zs)
         out = [None] * world
         dist.all_gather_object(out, dict(rank=rank, r0=sh.r0, r1=sh.r1, nnz=sh.nnz, y=ys.numpy(), z=zs.numpy(),
                                          xg=gathered.numpy(), x_block=sh.x_block))
@@ -92,7 +101,7 @@ def test_column_panels_partition_the_local_matrix():
     assert np.linalg.norm(y - want) <= 1e-13 * np.linalg.norm(want)
 
 
-@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_sharded_spmv_matches_single_process(world):
     rows = 4000
     ctx = mp.get_context("spawn")
@@ -157,7 +166,7 @@ def _cg_worker(rank, world, port, grid, iters, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_cg_converges_like_scipy(world):
     """Config 4's solver at toy size: 5-pt Laplacian (cg_example.c:71-128), b = 0.75*A*1, x0 = 0, plain CG."""
     import scipy.sparse as sp
