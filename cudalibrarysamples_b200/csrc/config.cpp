@@ -48,6 +48,12 @@ static int apply(Config& c, const char* key, const char* value) {
     }
     if (!strcmp(key, "B200SPMV_FLAT_QUIET")) { c.flat_quiet_permille = (value && value[0]) ? atoi(value) : 350; return 0; }
     if (!strcmp(key, "B200SPMV_SELL_GENERIC")) { c.sell_generic = truthy(value); return 0; }
+    if (!strcmp(key, "B200SPMV_GENERIC")) {
+        if (!value || !value[0] || !strcmp(value, "on") || !strcmp(value, "1")) c.generic = 1;
+        else if (!strcmp(value, "off") || !strcmp(value, "0")) c.generic = 0;
+        else return -1;
+        return 0;
+    }
     return -1;
 }
 
@@ -56,7 +62,7 @@ Config& config() {
     static std::once_flag once;
     std::call_once(once, [] {
         static const char* keys[] = {"B200SPMV_CSR_KERNEL", "B200SPMV_COO_KERNEL", "B200SPMV_TILE_ORDER", "B200SPMV_PDL",
-                                     "B200SPMV_SEG_DENSE", "B200SPMV_SELL_GENERIC", "B200SPMV_FLAT", "B200SPMV_FLAT_QUIET", "B200SPMV_SHORT"};
+                                     "B200SPMV_SEG_DENSE", "B200SPMV_SELL_GENERIC", "B200SPMV_FLAT", "B200SPMV_FLAT_QUIET", "B200SPMV_SHORT", "B200SPMV_GENERIC"};
         for (const char* k : keys)
             if (const char* v = getenv(k)) apply(c, k, v);
     });

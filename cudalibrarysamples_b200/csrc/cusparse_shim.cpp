@@ -7,8 +7,8 @@
 // cusparseSpMatSetAttribute (cg_example.c:396-402), cusparseDcsric02 ... -- while a side table remembers what our
 // kernels need (pointers, sizes, index base, SELL slice size: CUDA 12.9 has no cusparseSlicedEllGet).
 //
-// Anything we do not implement (transpose, 64-bit indices, mixed precision, complex, CSC/BSR/BlockedELL) is forwarded to
-// the real library, so nothing regresses.  B200SPMV_FORWARD=1 forwards everything (A/B runs with one binary).
+// Anything we do not implement (complex / 16-bit / integer value types, CSC/BSR/BlockedELL, CUSPARSE_SPMV_COO_ALG2) is
+// forwarded to the real library, so nothing regresses.  B200SPMV_FORWARD=1 forwards everything (A/B runs with one binary).
 #include <cuda_runtime_api.h>
 #include <cusparse.h>
 #include <dlfcn.h>
@@ -59,6 +59,8 @@ struct Real {
     REAL_FN(cusparseSpMM)
     REAL_FN(cusparseConstDnMatGet)
     REAL_FN(cusparseDnMatGetStridedBatch)
+    REAL_FN(cusparseCsrSetStridedBatch)
+    REAL_FN(cusparseSpMatGetStridedBatch)
 #undef REAL_FN
     bool forward = false, log = false;
 };
@@ -93,7 +95,8 @@ void init_real() {
     LOAD(cusparseSpMV_bufferSize) LOAD(cusparseSpMV_preprocess) LOAD(cusparseSpMV) LOAD(cusparseGetStream)
     LOAD(cusparseGetPointerMode) LOAD(cusparseSpMatGetFormat) LOAD(cusparseConstCsrGet) LOAD(cusparseConstCooGet)
     LOAD(cusparseConstDnVecGet) LOAD(cusparseSpMM_bufferSize) LOAD(cusparseSpMM_preprocess) LOAD(cusparseSpMM)
-    LOAD(cusparseConstDnMatGet) LOAD(cusparseDnMatGetStridedBatch)
+    LOAD(cusparseConstDnMatGet) LOAD(cusparseDnMatGetStridedBatch) LOAD(cusparseCsrSetStridedBatch)
+    LOAD(cusparseSpMatGetStridedBatch)
 #undef LOAD
     g_real = r;
 }
@@ -118,6 +121,8 @@ struct MatInfo {
     bool                 use_flat = false;       // preprocess built the flat plan and the row statistic favours csr_flat_kernel
     bool                 use_short = false;      // preprocess found no row longer than b200spmv_csr_short_max_row(): csr_short_kernel
     void*                plan_buffer = nullptr;  // externalBuffer holding this matrix' CSR plan: set ONLY by cusparseSpMV_preprocess
+    int                  batch = 1;              // cusparseCsrSetStridedBatch (spmm_csr_batched_example.c:140): matrices in the batch,
+    int64_t              off_stride = 0, colval_stride = 0;   //   element strides of the offsets / of the columns and values (0 = shared)
 };
 struct VecInfo {
     int64_t      size = 0;
@@ -183,20 +188,50 @@ void record_mat(const void* d, const MatInfo& m) {
 
 inline int dtype_of(cudaDataType t) { return t == CUDA_R_32F ? 0 : (t == CUDA_R_64F ? 1 : -1); }
 
-// Can our kernels take this call?  (Everything else is forwarded to the real library.)
-bool supported(cusparseOperation_t op, const MatInfo& m, const VecInfo& x, const VecInfo& y, cudaDataType compute, cusparseSpMVAlg_t alg) {
-    // A^T (== A^H for the real types served here): native for CSR (csr_transpose_kernel) and COO (the COO kernel with the
-    // index arrays swapped); Sliced-ELL transposes stay with the closed library
-    if (op != CUSPARSE_OPERATION_NON_TRANSPOSE && m.format == CUSPARSE_FORMAT_SLICED_ELLPACK) return false;
+// Which of our kernels take this call?  FAST: the specialised 32-bit-index, single-type kernels.  GENERIC: the plain kernels of
+// spmv_generic.cu (64-bit indices, fp32 A with fp64 x / y / arithmetic, Sliced-ELL transposes).  FORWARD: the closed library.
+enum Path { FORWARD = 0, FAST = 1, GENERIC = 2 };
+
+inline bool idx_ok(cusparseIndexType_t t) { return t == CUSPARSE_INDEX_32I || t == CUSPARSE_INDEX_64I; }
+
+Path classify(cusparseOperation_t op, const MatInfo& m, const VecInfo& x, const VecInfo& y, cudaDataType compute, cusparseSpMVAlg_t alg) {
+    if (m.format != CUSPARSE_FORMAT_CSR && m.format != CUSPARSE_FORMAT_COO && m.format != CUSPARSE_FORMAT_SLICED_ELLPACK) return FORWARD;
     // CUSPARSE_SPMV_COO_ALG2 promises bit-wise reproducible results (cusparse.h:5668-5677, cusparseSpMVAlg_t); our COO kernels add runs that
     // cross warps with floating-point atomics, so that request stays with the closed library.  (CSR / SELL kernels here are
     // reproducible for every alg value.)
-    if (m.format == CUSPARSE_FORMAT_COO && alg == CUSPARSE_SPMV_COO_ALG2) return false;
-    if (dtype_of(m.vtype) < 0 || x.vtype != m.vtype || y.vtype != m.vtype || compute != m.vtype) return false;
-    if (m.off_type != CUSPARSE_INDEX_32I || m.col_type != CUSPARSE_INDEX_32I) return false;
-    if (m.format != CUSPARSE_FORMAT_CSR && m.format != CUSPARSE_FORMAT_COO && m.format != CUSPARSE_FORMAT_SLICED_ELLPACK) return false;
-    if (m.rows >= INT32_MAX || m.cols >= INT32_MAX || m.nnz >= INT32_MAX - 65536) return false;
-    return true;
+    if (m.format == CUSPARSE_FORMAT_COO && alg == CUSPARSE_SPMV_COO_ALG2) return FORWARD;
+    const int a_dt = dtype_of(m.vtype), xy_dt = dtype_of(x.vtype);
+    if (a_dt < 0 || xy_dt < 0 || y.vtype != x.vtype || compute != x.vtype) return FORWARD;   // complex, 16-bit, integer types
+    const bool uniform = a_dt == xy_dt;
+    const bool idx32 = m.off_type == CUSPARSE_INDEX_32I && m.col_type == CUSPARSE_INDEX_32I;
+    const bool fits32 = m.rows < INT32_MAX && m.cols < INT32_MAX && m.nnz < INT32_MAX - 65536;
+    // A^T (== A^H for the real types served here): specialised for CSR (csr_transpose_kernel) and COO (the COO kernel with the
+    // index arrays swapped); Sliced-ELL transposes run on the generic kernel
+    const bool sell_t = op != CUSPARSE_OPERATION_NON_TRANSPOSE && m.format == CUSPARSE_FORMAT_SLICED_ELLPACK;
+    if (uniform && idx32 && fits32 && !sell_t) return FAST;
+    if (!b200::config().generic) return FORWARD;
+    if (a_dt > xy_dt) return FORWARD;                                   // fp64 A with fp32 vectors: not a cuSPARSE combination
+    if (!idx_ok(m.off_type) || !idx_ok(m.col_type)) return FORWARD;
+    if (m.off_type == CUSPARSE_INDEX_32I && m.col_type == CUSPARSE_INDEX_64I) return FORWARD;
+    return GENERIC;
+}
+
+// The call on the kernels of spmv_generic.cu (no plan, no workspace).
+int generic_mv(cudaStream_t stream, cusparseOperation_t op, const MatInfo& m, const VecInfo& x, const VecInfo& y, const void* alpha,
+               const void* beta, int on_dev) {
+    const int tr = op != CUSPARSE_OPERATION_NON_TRANSPOSE;
+    const int off64 = m.off_type == CUSPARSE_INDEX_64I, col64 = m.col_type == CUSPARSE_INDEX_64I;
+    const int a_dt = dtype_of(m.vtype), xy_dt = dtype_of(x.vtype);
+    if (m.format == CUSPARSE_FORMAT_CSR)
+        return b200spmv_csr_generic_mv((void*)stream, off64, col64, a_dt, xy_dt, tr, m.rows, m.cols, m.nnz, m.offsets, m.col_ind, m.values,
+                                       (int64_t)m.base, alpha, beta, on_dev, x.values, (void*)y.values);
+    if (m.format == CUSPARSE_FORMAT_COO)        // A^T: the same entry list with the index arrays (and the shape) swapped
+        return tr ? b200spmv_coo_generic_mv((void*)stream, col64, a_dt, xy_dt, m.cols, m.rows, m.nnz, m.col_ind, m.row_ind, m.values,
+                                            (int64_t)m.base, alpha, beta, on_dev, x.values, (void*)y.values)
+                  : b200spmv_coo_generic_mv((void*)stream, col64, a_dt, xy_dt, m.rows, m.cols, m.nnz, m.row_ind, m.col_ind, m.values,
+                                            (int64_t)m.base, alpha, beta, on_dev, x.values, (void*)y.values);
+    return b200spmv_sell_generic_mv((void*)stream, off64, col64, a_dt, xy_dt, tr, m.rows, m.cols, m.slice_size, m.offsets, m.col_ind,
+                                    m.values, (int64_t)m.base, alpha, beta, on_dev, x.values, (void*)y.values);
 }
 
 cusparseStatus_t to_status(int rc) {
@@ -365,6 +400,21 @@ cusparseStatus_t cusparseSpMatSetValues(cusparseSpMatDescr_t d, void* val) {
     return st;
 }
 
+// cusparse.h:5175 -- spmm_csr_batched_example.c:140.  The real descriptor keeps the setting (forwarded calls see it); the side
+// table remembers the strides, which the library offers no getter for.
+cusparseStatus_t cusparseCsrSetStridedBatch(cusparseSpMatDescr_t d, int batchCount, int64_t offsetsBatchStride,
+                                            int64_t columnsValuesBatchStride) {
+    cusparseStatus_t st = real().cusparseCsrSetStridedBatch(d, batchCount, offsetsBatchStride, columnsValuesBatchStride);
+    if (st == CUSPARSE_STATUS_SUCCESS) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_mats.find((const void*)d);
+        if (it != g_mats.end()) {
+            it->second.batch = batchCount; it->second.off_stride = offsetsBatchStride; it->second.colval_stride = columnsValuesBatchStride;
+        }
+    }
+    return st;
+}
+
 // ---------------------------------------------------------------- dense-vector descriptors ---------------------------
 cusparseStatus_t cusparseCreateDnVec(cusparseDnVecDescr_t* d, int64_t size, void* values, cudaDataType vT) {
     cusparseStatus_t st = real().cusparseCreateDnVec(d, size, values, vT);
@@ -416,8 +466,8 @@ cusparseStatus_t cusparseSpMV_bufferSize(cusparseHandle_t handle, cusparseOperat
     size_t real_size = 0;
     cusparseStatus_t st = R.cusparseSpMV_bufferSize(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, &real_size);
     MatInfo m; VecInfo x, y;
-    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType, alg)) {
-        *bufferSize = real_size;
+    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || classify(opA, m, x, y, computeType, alg) != FAST) {
+        *bufferSize = real_size;                   // forwarded calls need the real size; the generic kernels need nothing
         return st;
     }
     if (st != CUSPARSE_STATUS_SUCCESS) return st;  // the real library rejected the arguments: keep its verdict
@@ -460,11 +510,12 @@ cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t handle, cusparseOperat
     if (R.forward) return R.cusparseSpMV_preprocess(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
     if (!handle || !matA || !vecX || !vecY) return CUSPARSE_STATUS_INVALID_VALUE;
     MatInfo m; VecInfo x, y;
-    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType, alg))
+    Path path = FORWARD;
+    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || (path = classify(opA, m, x, y, computeType, alg)) == FORWARD)
         return R.cusparseSpMV_preprocess(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
     const bool tr = opA != CUSPARSE_OPERATION_NON_TRANSPOSE;
     if (x.size != (tr ? m.rows : m.cols) || y.size != (tr ? m.cols : m.rows)) return CUSPARSE_STATUS_INVALID_VALUE;
-    if (m.format != CUSPARSE_FORMAT_CSR || tr) return CUSPARSE_STATUS_SUCCESS;  // COO / SELL / A^T need no analysis
+    if (path == GENERIC || m.format != CUSPARSE_FORMAT_CSR || tr) return CUSPARSE_STATUS_SUCCESS;  // generic kernels / COO / SELL / A^T: no analysis
     if (!externalBuffer || ((uintptr_t)externalBuffer & 15)) return CUSPARSE_STATUS_INVALID_VALUE;
     cudaStream_t stream = nullptr;
     cusparseStatus_t st = R.cusparseGetStream(handle, &stream);
@@ -532,7 +583,8 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
     }
     if (!handle || !matA || !vecX || !vecY || !alpha || !beta) return CUSPARSE_STATUS_INVALID_VALUE;
     MatInfo m; VecInfo x, y;
-    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || !supported(opA, m, x, y, computeType, alg)) {
+    Path path = FORWARD;
+    if (!find_mat(matA, &m) || !find_vec(vecX, &x) || !find_vec(vecY, &y) || (path = classify(opA, m, x, y, computeType, alg)) == FORWARD) {
         if (R.log) fprintf(stderr, "[b200spmv] SpMV forwarded to libcusparse (unsupported combination)\n");
         b200::stats().forwarded_calls++;
         return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
@@ -548,7 +600,10 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
     const int on_dev = pm == CUSPARSE_POINTER_MODE_DEVICE;
     const int dt = dtype_of(m.vtype);
     int rc;
-    if (tr && m.format == CUSPARSE_FORMAT_CSR) {
+    if (path == GENERIC) {
+        logf("SpMV generic kernels (64-bit indices / mixed precision / Sliced-ELL transpose)", m);
+        rc = generic_mv(stream, opA, m, x, y, alpha, beta, on_dev);
+    } else if (tr && m.format == CUSPARSE_FORMAT_CSR) {
         logf("SpMV csr_transpose_kernel", m);
         rc = b200spmv_csr_transpose_mv((void*)stream, dt, m.rows, m.cols, m.nnz, m.offsets, m.col_ind, m.values, (int32_t)m.base, alpha,
                                        beta, on_dev, x.values, (void*)y.values);
@@ -559,8 +614,15 @@ cusparseStatus_t cusparseSpMV(cusparseHandle_t handle, cusparseOperation_t opA, 
     } else if (m.format == CUSPARSE_FORMAT_CSR) {
         if (m.rows == 0) return CUSPARSE_STATUS_SUCCESS;
         if (!externalBuffer || ((uintptr_t)externalBuffer & 15)) {
-            // No room for a plan (caller ignored bufferSize): let the real library handle it -- loudly under
-            // B200SPMV_LOG, and counted (b200spmv_get_stats) so a test can prove the hot path never takes this exit.
+            // No room for a plan (caller ignored bufferSize): the plan-free generic kernel serves it; with that kernel
+            // switched off the real library does -- loudly under B200SPMV_LOG, and counted (b200spmv_get_stats) so a test
+            // can prove the hot path never takes this exit.
+            if (b200::config().generic) {
+                logf("SpMV csr_generic_kernel (NULL or misaligned externalBuffer: no room for a plan)", m);
+                rc = generic_mv(stream, opA, m, x, y, alpha, beta, on_dev);
+                b200::stats().native_calls++;
+                return to_status(rc);
+            }
             if (R.log) fprintf(stderr, "[b200spmv] SpMV forwarded to libcusparse (NULL or misaligned externalBuffer)\n");
             b200::stats().forwarded_calls++;
             return R.cusparseSpMV(handle, opA, alpha, matA, vecX, beta, vecY, computeType, alg, externalBuffer);
@@ -608,20 +670,33 @@ struct DnMatInfo {
     cudaDataType vtype = CUDA_R_32F;
     cusparseOrder_t order = CUSPARSE_ORDER_COL;
     int batch = 1;
+    int64_t stride = 0;          // elements between consecutive matrices of a strided batch (cusparseDnMatSetStridedBatch)
 };
 static bool get_dnmat(cusparseConstDnMatDescr_t d, DnMatInfo* m) {
     Real& R = real();
     if (R.cusparseConstDnMatGet(d, &m->rows, &m->cols, &m->ld, &m->values, &m->vtype, &m->order) != CUSPARSE_STATUS_SUCCESS) return false;
-    int64_t stride = 0;
-    if (R.cusparseDnMatGetStridedBatch(d, &m->batch, &stride) != CUSPARSE_STATUS_SUCCESS) m->batch = 1;
+    if (R.cusparseDnMatGetStridedBatch(d, &m->batch, &m->stride) != CUSPARSE_STATUS_SUCCESS) { m->batch = 1; m->stride = 0; }
+    if (m->batch < 1) m->batch = 1;
     return true;
+}
+// Strided batches (spmm_csr_batched_example.c:138-160): C_i = alpha * A_i * B_i + beta * C_i for i < N, every operand either
+// strided with N entries or shared by the whole batch (A with both strides 0: the sample's "matA broadcast" variant; B with
+// batch count 1).  Returns N (1 = no batch), or 0 for a combination we leave to the real library.
+static int spmm_batch_count(cusparseConstSpMatDescr_t matA, const MatInfo& a, const DnMatInfo& b, const DnMatInfo& c) {
+    int real_a = 1;
+    if (real().cusparseSpMatGetStridedBatch(matA, &real_a) != CUSPARSE_STATUS_SUCCESS || real_a < 1) real_a = 1;
+    if (real_a != (a.batch < 1 ? 1 : a.batch)) return 0;      // the batch was set behind our back: we do not know its strides
+    const int n = c.batch;
+    if (real_a != 1 && real_a != n) return 0;
+    if (b.batch != 1 && b.batch != n) return 0;
+    if (n > 1 && c.stride < c.rows * c.cols) return 0;        // overlapping outputs
+    return n;
 }
 static bool spmm_supported(cusparseOperation_t opA, cusparseOperation_t opB, const MatInfo& a, const DnMatInfo& b, const DnMatInfo& c,
                            cudaDataType compute) {
     if (opA != CUSPARSE_OPERATION_NON_TRANSPOSE || opB != CUSPARSE_OPERATION_NON_TRANSPOSE) return false;
     if (a.format != CUSPARSE_FORMAT_CSR || a.off_type != CUSPARSE_INDEX_32I || a.col_type != CUSPARSE_INDEX_32I) return false;
     if (dtype_of(a.vtype) < 0 || b.vtype != a.vtype || c.vtype != a.vtype || compute != a.vtype) return false;
-    if (b.batch > 1 || c.batch > 1) return false;                    // strided batches (spmm_csr_batched) stay with the real library
     if (a.rows >= INT32_MAX || a.cols >= INT32_MAX || a.nnz >= INT32_MAX - 65536 || c.cols >= 64 * 65535) return false;
     return true;
 }
@@ -635,7 +710,7 @@ cusparseStatus_t cusparseSpMM_bufferSize(cusparseHandle_t handle, cusparseOperat
     cusparseStatus_t st = R.cusparseSpMM_bufferSize(handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg, bufferSize);
     MatInfo a; DnMatInfo b, c;
     if (st == CUSPARSE_STATUS_SUCCESS && !R.forward && bufferSize && handle && matA && matB && matC && find_mat(matA, &a) &&
-        get_dnmat(matB, &b) && get_dnmat(matC, &c) && spmm_supported(opA, opB, a, b, c, computeType)) {
+        get_dnmat(matB, &b) && get_dnmat(matC, &c) && spmm_supported(opA, opB, a, b, c, computeType) && spmm_batch_count(matA, a, b, c) > 0) {
         const size_t ours = b200spmm_csr_workspace_bytes(dtype_of(a.vtype), b.rows, b.cols, b.order == CUSPARSE_ORDER_ROW);
         if (ours > *bufferSize) *bufferSize = ours;
     }
@@ -649,7 +724,7 @@ cusparseStatus_t cusparseSpMM_preprocess(cusparseHandle_t handle, cusparseOperat
     Real& R = real();
     MatInfo a; DnMatInfo b, c;
     if (!R.forward && handle && matA && matB && matC && find_mat(matA, &a) && get_dnmat(matB, &b) && get_dnmat(matC, &c) &&
-        spmm_supported(opA, opB, a, b, c, computeType))
+        spmm_supported(opA, opB, a, b, c, computeType) && spmm_batch_count(matA, a, b, c) > 0)
         return CUSPARSE_STATUS_SUCCESS;                              // nothing to analyse
     return R.cusparseSpMM_preprocess(handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg, externalBuffer);
 }
@@ -659,8 +734,9 @@ cusparseStatus_t cusparseSpMM(cusparseHandle_t handle, cusparseOperation_t opA, 
                               cusparseDnMatDescr_t matC, cudaDataType computeType, cusparseSpMMAlg_t alg, void* externalBuffer) {
     Real& R = real();
     MatInfo a; DnMatInfo b, c;
+    int nbatch = 0;
     if (R.forward || !handle || !matA || !matB || !matC || !alpha || !beta || !find_mat(matA, &a) || !get_dnmat(matB, &b) ||
-        !get_dnmat(matC, &c) || !spmm_supported(opA, opB, a, b, c, computeType)) {
+        !get_dnmat(matC, &c) || !spmm_supported(opA, opB, a, b, c, computeType) || (nbatch = spmm_batch_count(matA, a, b, c)) == 0) {
         if (R.log) fprintf(stderr, "[b200spmv] SpMM forwarded to libcusparse\n");
         b200::stats().forwarded_calls++;
         return R.cusparseSpMM(handle, opA, opB, alpha, matA, matB, beta, matC, computeType, alg, externalBuffer);
@@ -672,12 +748,20 @@ cusparseStatus_t cusparseSpMM(cusparseHandle_t handle, cusparseOperation_t opA, 
     cusparsePointerMode_t pm = CUSPARSE_POINTER_MODE_HOST;
     st = R.cusparseGetPointerMode(handle, &pm);
     if (st != CUSPARSE_STATUS_SUCCESS) return st;
-    if (R.log) fprintf(stderr, "[b200spmv] SpMM spmm_csr_kernel rows=%lld cols=%lld n=%lld nnz=%lld\n", (long long)a.rows,
-                       (long long)a.cols, (long long)c.cols, (long long)a.nnz);
-    // externalBuffer: sized by our cusparseSpMM_bufferSize (>= the row-major copy of a column-major B); NULL -> strided walk
-    const int rc = b200spmm_csr_ws((void*)stream, dtype_of(a.vtype), a.rows, a.cols, c.cols, a.nnz, a.offsets, a.col_ind, a.values,
-                                   (int32_t)a.base, alpha, beta, pm == CUSPARSE_POINTER_MODE_DEVICE, b.values, b.ld,
-                                   b.order == CUSPARSE_ORDER_ROW, (void*)c.values, c.ld, c.order == CUSPARSE_ORDER_ROW, externalBuffer);
+    if (R.log) fprintf(stderr, "[b200spmv] SpMM spmm_csr_kernel rows=%lld cols=%lld n=%lld nnz=%lld batch=%d\n", (long long)a.rows,
+                       (long long)a.cols, (long long)c.cols, (long long)a.nnz, nbatch);
+    // externalBuffer: sized by our cusparseSpMM_bufferSize (>= the row-major copy of a column-major B); NULL -> strided walk.
+    // A strided batch is one launch sequence per matrix on the handle's stream (the row-major copy of B_i in the buffer is
+    // consumed by product i before product i+1 overwrites it: stream order).
+    const size_t vsz = a.vtype == CUDA_R_64F ? 8 : 4;
+    const int64_t a_off = a.batch > 1 ? a.off_stride : 0, a_cv = a.batch > 1 ? a.colval_stride : 0, b_st = b.batch > 1 ? b.stride : 0;
+    int rc = 0;
+    for (int i = 0; i < nbatch && rc == 0; i++)
+        rc = b200spmm_csr_ws((void*)stream, dtype_of(a.vtype), a.rows, a.cols, c.cols, a.nnz, (const char*)a.offsets + (size_t)i * a_off * 4,
+                             (const char*)a.col_ind + (size_t)i * a_cv * 4, (const char*)a.values + (size_t)i * a_cv * vsz, (int32_t)a.base,
+                             alpha, beta, pm == CUSPARSE_POINTER_MODE_DEVICE, (const char*)b.values + (size_t)i * b_st * vsz, b.ld,
+                             b.order == CUSPARSE_ORDER_ROW, (char*)c.values + (size_t)i * c.stride * vsz, c.ld,
+                             c.order == CUSPARSE_ORDER_ROW, externalBuffer);
     b200::stats().native_calls++;
     return to_status(rc);
 }

@@ -41,6 +41,7 @@ CUDA_R_64F = 1
 CUSPARSE_ORDER_COL = 1
 CUSPARSE_ORDER_ROW = 2
 CUSPARSE_SPMM_ALG_DEFAULT = 0
+CUSPARSE_SPMM_CSR_ALG2 = 6
 
 _VT = {torch.float32: CUDA_R_32F, torch.float64: CUDA_R_64F}
 _IT = {torch.int32: CUSPARSE_INDEX_32I, torch.int64: CUSPARSE_INDEX_64I}
@@ -168,6 +169,14 @@ class Api:
                    C.c_int(_VT[values.dtype]), C.c_int(order))
         return d
 
+    def cusparseDnMatSetStridedBatch(self, d, batchCount, batchStride):
+        self._call(self.real, "cusparseDnMatSetStridedBatch", d, C.c_int(batchCount), C.c_int64(batchStride))
+
+    def cusparseCsrSetStridedBatch(self, d, batchCount, offsetsBatchStride, columnsValuesBatchStride):
+        """spmm_csr_batched_example.c:140 (strides in elements; 0 = the array is shared by the whole batch)."""
+        self._call(self.lib, "cusparseCsrSetStridedBatch", d, C.c_int(batchCount), C.c_int64(offsetsBatchStride),
+                   C.c_int64(columnsValuesBatchStride))
+
     def cusparseDestroyDnMat(self, d):
         self._call(self.real, "cusparseDestroyDnMat", d)
 
@@ -235,14 +244,17 @@ class SpMVOperator:
     (cg_example.c:387-418 keeps matA / d_bufferMV for the whole solve and calls cusparseSpMV per iteration)."""
 
     def __init__(self, api: Api, fmt: str, rows: int, cols: int, arrays: dict, base: int = 0, preprocess: bool = True,
-                 alg: int = CUSPARSE_SPMV_ALG_DEFAULT, handle=None, op: int = CUSPARSE_OPERATION_NON_TRANSPOSE):
+                 alg: int = CUSPARSE_SPMV_ALG_DEFAULT, handle=None, op: int = CUSPARSE_OPERATION_NON_TRANSPOSE,
+                 xy_dtype: torch.dtype | None = None):
+        """xy_dtype: type of x, y, alpha, beta and of the arithmetic when it differs from the type of A's values (mixed
+        precision: fp32 A with fp64 vectors); index widths follow the dtypes of the index tensors (int32 / int64)."""
         self.api, self.fmt, self.rows, self.cols, self.base, self.alg, self.op = api, fmt, rows, cols, base, alg, op
         self.arrays = arrays  # keeps the device tensors alive
         self.own_handle = handle is None
         self.handle = api.cusparseCreate() if handle is None else handle
         val = arrays["val"]
-        self.dtype = val.dtype
-        self.ctype = _VT[val.dtype]
+        self.dtype = xy_dtype or val.dtype      # the type of x / y / the scalars / the arithmetic
+        self.ctype = _VT[self.dtype]
         if fmt == "csr":
             self.nnz = int(arrays["col"].numel())
             self.mat = api.cusparseCreateCsr(rows, cols, self.nnz, arrays["off"], arrays["col"], val, base)
@@ -256,8 +268,8 @@ class SpMVOperator:
         else:
             raise ValueError(fmt)
         nx, ny = (cols, rows) if op == CUSPARSE_OPERATION_NON_TRANSPOSE else (rows, cols)      # A^T: y[cols] = A^T x[rows]
-        self._x = torch.empty(max(nx, 1), dtype=val.dtype, device=val.device)
-        self._y = torch.empty(max(ny, 1), dtype=val.dtype, device=val.device)
+        self._x = torch.empty(max(nx, 1), dtype=self.dtype, device=val.device)
+        self._y = torch.empty(max(ny, 1), dtype=self.dtype, device=val.device)
         self.vecX = api.cusparseCreateDnVec(nx, self._x)
         self.vecY = api.cusparseCreateDnVec(ny, self._y)
         size = api.cusparseSpMV_bufferSize(self.handle, op, 1.0, self.mat, self.vecX, 0.0,
@@ -339,6 +351,40 @@ def spmm(api: Api, rows: int, cols: int, arrays: dict, B: torch.Tensor, C0: torc
     api.cusparseSpMM(h, op, op, alpha, matA, matB, beta, matC, ct, CUSPARSE_SPMM_ALG_DEFAULT, buf)
     if timing is not None:
         timing[1].record()
+    torch.cuda.synchronize()
+    api.cusparseDestroySpMat(matA)
+    api.cusparseDestroyDnMat(matB)
+    api.cusparseDestroyDnMat(matC)
+    api.cusparseDestroy(h)
+    return Cb
+
+
+def spmm_batched(api: Api, rows: int, cols: int, nnz: int, batches: int, off: torch.Tensor, col: torch.Tensor, val: torch.Tensor,
+                 B: torch.Tensor, C0: torch.Tensor, alpha=1.0, beta=0.0, off_stride: int = 0, colval_stride: int | None = None,
+                 b_stride: int | None = None, order: int = CUSPARSE_ORDER_COL) -> torch.Tensor:
+    """The call sequence of cuSPARSE/spmm_csr_batched/spmm_csr_batched_example.c:128-160: C_i = alpha*A_i*B_i + beta*C_i.
+
+    off / col / val hold the batch back to back with the given element strides (off_stride 0: shared row offsets, as in the
+    sample; colval_stride 0: the whole matrix shared, the sample's "matA broadcast" variant); B and C0 are 1-D buffers of
+    `batches` dense matrices with the tight leading dimension (b_stride 0: B shared)."""
+    n = C0.numel() // (batches * max(rows, 1))
+    ct = _VT[val.dtype]
+    colval_stride = nnz if colval_stride is None else colval_stride
+    b_stride = cols * n if b_stride is None else b_stride
+    h = api.cusparseCreate()
+    matA = api.cusparseCreateCsr(rows, cols, nnz, off, col, val)
+    api.cusparseCsrSetStridedBatch(matA, batches, off_stride, colval_stride)
+    Cb = C0.clone()
+    matB = api.cusparseCreateDnMat(cols, n, cols if order == CUSPARSE_ORDER_COL else n, B, order)
+    if b_stride:
+        api.cusparseDnMatSetStridedBatch(matB, batches, b_stride)
+    matC = api.cusparseCreateDnMat(rows, n, rows if order == CUSPARSE_ORDER_COL else n, Cb, order)
+    api.cusparseDnMatSetStridedBatch(matC, batches, rows * n)
+    op = CUSPARSE_OPERATION_NON_TRANSPOSE
+    alg = CUSPARSE_SPMM_CSR_ALG2                        # as in the sample (:150,157)
+    size = api.cusparseSpMM_bufferSize(h, op, op, alpha, matA, matB, beta, matC, ct, alg)
+    buf = torch.empty(max(size, 16), dtype=torch.uint8, device=val.device)
+    api.cusparseSpMM(h, op, op, alpha, matA, matB, beta, matC, ct, alg, buf)
     torch.cuda.synchronize()
     api.cusparseDestroySpMat(matA)
     api.cusparseDestroyDnMat(matB)

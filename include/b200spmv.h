@@ -163,11 +163,32 @@ B200SPMV_EXPORT int    b200spmv_sell_mv(void* stream, int dtype, int64_t rows, i
                                         int32_t base, const void* alpha, const void* beta, int scalars_on_device,
                                         const void* x, void* y, void* workspace);
 
+/* The long tail of cusparseSpMV's real-valued argument space (spmv_generic.cu): 64-bit indices, fp32 A with
+ * fp64 x / y / arithmetic, transposes of those and of Sliced-ELL, CSR without a workspace.  Plain plan-free kernels.
+ *   off64 / col64 / idx64 : 0 = int32, 1 = int64 (CUSPARSE_INDEX_32I / _64I, cusparse.h:5002-5007); 32-bit offsets with 64-bit
+ *                           columns are rejected (-1)
+ *   a_dtype               : type of A's values; xy_dtype: type of x, y, alpha, beta and of the arithmetic (0 = fp32, 1 = fp64);
+ *                           a_dtype <= xy_dtype
+ *   transpose             : 0: y[rows] = alpha*A*x[cols] + beta*y;  1: y[cols] = alpha*A^T*x[rows] + beta*y (fp atomics)
+ * COO: A^T is the same call with row_ind / col_ind and rows / cols swapped. */
+B200SPMV_EXPORT int b200spmv_csr_generic_mv(void* stream, int off64, int col64, int a_dtype, int xy_dtype, int transpose,
+                                            int64_t rows, int64_t cols, int64_t nnz, const void* row_offsets, const void* col_ind,
+                                            const void* values, int64_t base, const void* alpha, const void* beta,
+                                            int scalars_on_device, const void* x, void* y);
+B200SPMV_EXPORT int b200spmv_coo_generic_mv(void* stream, int idx64, int a_dtype, int xy_dtype, int64_t rows, int64_t cols,
+                                            int64_t nnz, const void* row_ind, const void* col_ind, const void* values, int64_t base,
+                                            const void* alpha, const void* beta, int scalars_on_device, const void* x, void* y);
+B200SPMV_EXPORT int b200spmv_sell_generic_mv(void* stream, int off64, int col64, int a_dtype, int xy_dtype, int transpose,
+                                             int64_t rows, int64_t cols, int64_t slice_size, const void* slice_offsets,
+                                             const void* col_ind, const void* values, int64_t base, const void* alpha,
+                                             const void* beta, int scalars_on_device, const void* x, void* y);
+
 /* Run-time switches (tests / tuning sweeps; never needed by a caller).  The environment variables of the same names
  * are read ONCE at first use; afterwards only this call changes them.  Not thread-safe against concurrent launches.
  *   B200SPMV_CSR_KERNEL = auto|tile|pipe|ws|rowwise|seg     B200SPMV_COO_KERNEL = auto|tile|seg
  *   B200SPMV_FLAT = auto|on|off   B200SPMV_FLAT_QUIET = <permille>
  *   B200SPMV_TILE_ORDER = scatter|linear   B200SPMV_PDL = 0|1   B200SPMV_SEG_DENSE = <nnz per row>   B200SPMV_SELL_GENERIC = 0|1
+ *   B200SPMV_SHORT = auto|on|off   B200SPMV_GENERIC = on|off (off: what spmv_generic.cu serves goes to the closed library)
  * returns 0, or -1 for an unknown key / value. */
 B200SPMV_EXPORT int  b200spmv_set_option(const char* key, const char* value);
 /* Call counters of the cuSPARSE-symbol layer: SpMV calls that ran on our kernels, SpMV calls handed to the closed library
@@ -223,6 +244,8 @@ B200SPMV_EXPORT cusparseStatus_t cusparseDestroySpMat(cusparseConstSpMatDescr_t)
 B200SPMV_EXPORT cusparseStatus_t cusparseCsrSetPointers(cusparseSpMatDescr_t, void*, void*, void*);
 B200SPMV_EXPORT cusparseStatus_t cusparseCooSetPointers(cusparseSpMatDescr_t, void*, void*, void*);
 B200SPMV_EXPORT cusparseStatus_t cusparseSpMatSetValues(cusparseSpMatDescr_t, void*);
+/* cusparse.h:5175 -- spmm_csr_batched_example.c:140 (the library has no getter for the strides: the shim records them) */
+B200SPMV_EXPORT cusparseStatus_t cusparseCsrSetStridedBatch(cusparseSpMatDescr_t, int, int64_t, int64_t);
 /* cusparse.h:5094 / 5100 / 5106 / 5129 -- spmv_csr_example.c:93-95,116-117, cg_example.c:371-378 */
 B200SPMV_EXPORT cusparseStatus_t cusparseCreateDnVec(cusparseDnVecDescr_t*, int64_t, void*, cudaDataType);
 B200SPMV_EXPORT cusparseStatus_t cusparseCreateConstDnVec(cusparseConstDnVecDescr_t*, int64_t, const void*, cudaDataType);
@@ -241,8 +264,9 @@ B200SPMV_EXPORT cusparseStatus_t cusparseSpMV_preprocess(cusparseHandle_t, cuspa
 B200SPMV_EXPORT cusparseStatus_t cusparseSpMV(cusparseHandle_t, cusparseOperation_t, const void*, cusparseConstSpMatDescr_t,
                                               cusparseConstDnVecDescr_t, const void*, cusparseDnVecDescr_t, cudaDataType,
                                               cusparseSpMVAlg_t, void*);
-/* cusparse.h:5862-5898 -- spmm_csr_example.c:105-132 (dense-matrix descriptors stay with the real library: the shim reads
- * them through cusparseConstDnMatGet, so cusparseCreateDnMat / cusparseDestroyDnMat need no re-export) */
+/* cusparse.h:5862-5898 -- spmm_csr_example.c:105-132, spmm_csr_batched_example.c:138-160 (dense-matrix descriptors stay with
+ * the real library: the shim reads them through cusparseConstDnMatGet / cusparseDnMatGetStridedBatch, so cusparseCreateDnMat /
+ * cusparseDnMatSetStridedBatch / cusparseDestroyDnMat need no re-export) */
 B200SPMV_EXPORT cusparseStatus_t cusparseSpMM_bufferSize(cusparseHandle_t, cusparseOperation_t, cusparseOperation_t, const void*,
                                                          cusparseConstSpMatDescr_t, cusparseConstDnMatDescr_t, const void*,
                                                          cusparseDnMatDescr_t, cudaDataType, cusparseSpMMAlg_t, size_t*);

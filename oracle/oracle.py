@@ -256,3 +256,15 @@ TOY = dict(
     spmm_B=np.arange(1, 13, dtype=np.float32).reshape(3, 4).T.copy(),
     spmm_C=np.array([19, 8, 51, 52, 43, 24, 123, 120, 67, 40, 195, 188], np.float32).reshape(3, 4).T.copy(),
 )
+
+# The strided-batch variant of the toy product (cuSPARSE/spmm_csr_batched/spmm_csr_batched_example.c:56-88): two 4x4 matrices
+# sharing the row offsets (:56), columns / values per batch (:57-67), B per batch (:68-73), golden C per batch (:80-85), all
+# dense operands column-major 4x3; the sample compares with `!=` (:183-196).
+TOY_BATCHED = dict(
+    rows=4, cols=4, nnz=9, n=3, batches=2,
+    csr_off=np.array([0, 3, 4, 7, 9], np.int32),
+    csr_col=np.array([[0, 2, 3, 1, 0, 2, 3, 1, 3], [1, 2, 3, 0, 0, 1, 3, 1, 2]], np.int32),
+    val=np.array([[1, 2, 3, 4, 5, 6, 7, 8, 9], [10, 11, 12, 13, 14, 15, 16, 17, 18]], np.float32),
+    B=np.array([[1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12], [6, 4, 3, 2, 1, 6, 9, 8, 9, 3, 2, 5]], np.float32),          # column-major buffers
+    C=np.array([[19, 8, 51, 52, 43, 24, 123, 120, 67, 40, 195, 188], [97, 78, 176, 122, 255, 13, 232, 264, 112, 117, 251, 87]], np.float32),
+)

@@ -146,3 +146,12 @@ def test_spmm_golden_of_the_reference_sample():
     B, C0 = rng.uniform(-1, 1, (500, 7)), rng.uniform(-1, 1, (500, 7))
     got = O.spmm_csr(off, col, val, B, C0, alpha=-0.5, beta=2.0, order_b="row", order_c="col", threads=2)
     assert np.allclose(got, -0.5 * (A @ B) + 2.0 * C0, rtol=1e-13, atol=1e-13)
+
+
+def test_spmm_batched_golden_of_the_reference_sample():
+    """cuSPARSE/spmm_csr_batched/spmm_csr_batched_example.c:56-88: two products sharing the row offsets; hC1_result / hC2_result."""
+    T = O.TOY_BATCHED
+    for i in range(T["batches"]):
+        B = T["B"][i].reshape(T["n"], T["cols"]).T              # the column-major 4x3 buffer as a 2-D array
+        C = O.spmm_csr(T["csr_off"], T["csr_col"][i], T["val"][i], B)
+        assert np.array_equal(np.asfortranarray(C).T.reshape(-1), T["C"][i]), i
