@@ -62,14 +62,25 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def kernel_source_sha():
-    """Hash of the kernel sources: profiles/traffic.json is only quoted when it was captured from THIS code."""
-    h = hashlib.sha256()
+def kernel_source_sha(kernel="b200::csr_flat_kernel<double>"):
+    """Hash of what `kernel` is compiled from: the .cu file under csrc/ that defines it, the device-code header every kernel
+    file includes (spmv_common.cuh) and the nvcc flags.  profiles/traffic.json is only quoted when it was captured from THIS
+    code; host-side files (the shim, the run-time options) and the other kernels' files do not change the kernel's SASS and do
+    not invalidate the capture (checked for the round-2 capture: the SASS of spmv_csr_flat.cu built from the capture's commit
+    and from this tree is byte-identical, profiles/README.md)."""
+    from cudalibrarysamples_b200 import build as B
     d = os.path.join(ROOT, "cudalibrarysamples_b200", "csrc")
+    short = kernel.split("::")[-1].split("<")[0]
+    owner = None
     for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".cpp", ".h")):
-            h.update(name.encode())
-            h.update(open(os.path.join(d, name), "rb").read())
+        if name.endswith(".cu") and ("__global__" in open(os.path.join(d, name)).read()) and (" " + short + "(") in open(os.path.join(d, name)).read():
+            owner = name
+            break
+    h = hashlib.sha256()
+    for name in ([owner] if owner else []) + ["spmv_common.cuh"]:
+        h.update(name.encode())
+        h.update(open(os.path.join(d, name), "rb").read())
+    h.update(" ".join(B.NVCC_FLAGS).encode())
     return h.hexdigest()[:16]
 
 
@@ -765,7 +776,7 @@ def run_ours(args):
         if os.path.exists(prof):
             try:
                 t = json.load(open(prof))
-                if t.get("source_sha") == kernel_source_sha() and t.get("kernel") == kname and world == 1:
+                if t.get("kernel") == kname and t.get("source_sha") == kernel_source_sha(kname) and world == 1:
                     line["roofline"]["traffic"] = t.get("dram_bytes_per_launch")
                     line["roofline"]["traffic_source"] = t.get("ncu_report")
                 else:

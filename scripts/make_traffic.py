@@ -24,7 +24,7 @@ unit = rows[1][hdr.index("dram__bytes_read.sum")]
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
 unit_w = rows[1][hdr.index("dram__bytes_write.sum")]
 scale_w = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit_w]
-rec = {"source_sha": kernel_source_sha(), "kernel": kernel, "workload": "R-MAT 1M x 1M, 16M nnz, fp64 (BASELINE.json configs[1])",
+rec = {"source_sha": kernel_source_sha(kernel), "source_sha_of": "the .cu file defining the kernel + spmv_common.cuh + nvcc flags (bench.py kernel_source_sha)", "kernel": kernel, "workload": "R-MAT 1M x 1M, 16M nnz, fp64 (BASELINE.json configs[1])",
        "dram_bytes_per_launch": int(rd * scale + wr * scale_w), "dram_read_bytes": int(rd * scale), "dram_write_bytes": int(wr * scale_w),
        "kernel_time_us_under_ncu": float(r[hdr.index("gpu__time_duration.sum")]), "ncu_report": os.path.relpath(rep, ROOT)}
 json.dump(rec, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
