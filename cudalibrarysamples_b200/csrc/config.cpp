@@ -49,8 +49,9 @@ static int apply(Config& c, const char* key, const char* value) {
     if (!strcmp(key, "B200SPMV_FLAT_QUIET")) { c.flat_quiet_permille = (value && value[0]) ? atoi(value) : 350; return 0; }
     if (!strcmp(key, "B200SPMV_SELL_GENERIC")) { c.sell_generic = truthy(value); return 0; }
     if (!strcmp(key, "B200SPMV_GENERIC")) {
-        if (!value || !value[0] || !strcmp(value, "on") || !strcmp(value, "1")) c.generic = 1;
+        if (!value || !value[0] || !strcmp(value, "csr") || !strcmp(value, "on") || !strcmp(value, "1")) c.generic = 1;
         else if (!strcmp(value, "off") || !strcmp(value, "0")) c.generic = 0;
+        else if (!strcmp(value, "all") || !strcmp(value, "2")) c.generic = 2;
         else return -1;
         return 0;
     }

@@ -14,8 +14,12 @@ struct Config {
     int flat_quiet_permille = 350;   // B200SPMV_FLAT_QUIET: auto picks the flat kernel when at least this share of the 32-non-zero steps ends no row
     int short_rows  = -1;   // B200SPMV_SHORT = auto|on|off: csr_short_kernel (warp per 32 rows); auto = preprocess found no row longer than 32
     int coo_kernel  = -1;   // B200SPMV_COO_KERNEL = tile|seg ; -1 = default (seg)
-    int generic     = 1;    // B200SPMV_GENERIC = on|off: spmv_generic.cu serves 64-bit indices / fp32 A with fp64 vectors / Sliced-ELL
-                            //                    transposes / CSR calls without a buffer; off = those go to the closed library
+    int generic     = 1;    // B200SPMV_GENERIC = off|csr|all: what spmv_generic.cu serves instead of the closed library.
+                            //   csr (default): CSR with 64-bit indices / fp32 A with fp64 vectors / their transposes / no buffer --
+                            //                  validated on B200 (tests/test_generic_gpu.py, round 2 call N);
+                            //   all: also COO and Sliced-ELL of those kinds, Sliced-ELL transposes, strided-batch SpMM -- written
+                            //        and emulated on the CPU, their first hardware run is tests/test_zz_unverified_gpu.py;
+                            //   off: everything of that kind goes to the closed library
 };
 
 Config& config();

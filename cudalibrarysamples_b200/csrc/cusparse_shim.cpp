@@ -190,6 +190,7 @@ inline int dtype_of(cudaDataType t) { return t == CUDA_R_32F ? 0 : (t == CUDA_R_
 
 // Which of our kernels take this call?  FAST: the specialised 32-bit-index, single-type kernels.  GENERIC: the plain kernels of
 // spmv_generic.cu (64-bit indices, fp32 A with fp64 x / y / arithmetic, Sliced-ELL transposes).  FORWARD: the closed library.
+// (COO / Sliced-ELL on the generic kernels: only with B200SPMV_GENERIC=all, see config.h.)
 enum Path { FORWARD = 0, FAST = 1, GENERIC = 2 };
 
 inline bool idx_ok(cusparseIndexType_t t) { return t == CUSPARSE_INDEX_32I || t == CUSPARSE_INDEX_64I; }
@@ -209,7 +210,8 @@ Path classify(cusparseOperation_t op, const MatInfo& m, const VecInfo& x, const 
     // index arrays swapped); Sliced-ELL transposes run on the generic kernel
     const bool sell_t = op != CUSPARSE_OPERATION_NON_TRANSPOSE && m.format == CUSPARSE_FORMAT_SLICED_ELLPACK;
     if (uniform && idx32 && fits32 && !sell_t) return FAST;
-    if (!b200::config().generic) return FORWARD;
+    const int generic = b200::config().generic;      // 0 off, 1 CSR only (validated on hardware), 2 also COO / Sliced-ELL
+    if (generic == 0 || (generic == 1 && m.format != CUSPARSE_FORMAT_CSR)) return FORWARD;
     if (a_dt > xy_dt) return FORWARD;                                   // fp64 A with fp32 vectors: not a cuSPARSE combination
     if (!idx_ok(m.off_type) || !idx_ok(m.col_type)) return FORWARD;
     if (m.off_type == CUSPARSE_INDEX_32I && m.col_type == CUSPARSE_INDEX_64I) return FORWARD;
@@ -687,6 +689,7 @@ static int spmm_batch_count(cusparseConstSpMatDescr_t matA, const MatInfo& a, co
     if (real().cusparseSpMatGetStridedBatch(matA, &real_a) != CUSPARSE_STATUS_SUCCESS || real_a < 1) real_a = 1;
     if (real_a != (a.batch < 1 ? 1 : a.batch)) return 0;      // the batch was set behind our back: we do not know its strides
     const int n = c.batch;
+    if ((real_a > 1 || b.batch > 1 || n > 1) && b200::config().generic < 2) return 0;   // batches: opt-in until run on hardware (config.h)
     if (real_a != 1 && real_a != n) return 0;
     if (b.batch != 1 && b.batch != n) return 0;
     if (n > 1 && c.stride < c.rows * c.cols) return 0;        // overlapping outputs

@@ -188,7 +188,9 @@ B200SPMV_EXPORT int b200spmv_sell_generic_mv(void* stream, int off64, int col64,
  *   B200SPMV_CSR_KERNEL = auto|tile|pipe|ws|rowwise|seg     B200SPMV_COO_KERNEL = auto|tile|seg
  *   B200SPMV_FLAT = auto|on|off   B200SPMV_FLAT_QUIET = <permille>
  *   B200SPMV_TILE_ORDER = scatter|linear   B200SPMV_PDL = 0|1   B200SPMV_SEG_DENSE = <nnz per row>   B200SPMV_SELL_GENERIC = 0|1
- *   B200SPMV_SHORT = auto|on|off   B200SPMV_GENERIC = on|off (off: what spmv_generic.cu serves goes to the closed library)
+ *   B200SPMV_SHORT = auto|on|off
+ *   B200SPMV_GENERIC = off|csr|all (what spmv_generic.cu serves instead of the closed library: nothing / CSR [default] / also
+ *                      COO, Sliced-ELL and strided-batch SpMM, which have not had their first hardware run yet)
  * returns 0, or -1 for an unknown key / value. */
 B200SPMV_EXPORT int  b200spmv_set_option(const char* key, const char* value);
 /* Call counters of the cuSPARSE-symbol layer: SpMV calls that ran on our kernels, SpMV calls handed to the closed library

@@ -53,6 +53,9 @@ def test_options_are_set_through_the_abi_not_the_environment(built_lib):
     assert lib.b200spmv_set_option(b"B200SPMV_CSR_KERNEL", b"auto") == 0
     assert lib.b200spmv_set_option(b"B200SPMV_CSR_KERNEL", b"no-such-kernel") == -1
     assert lib.b200spmv_set_option(b"NO_SUCH_KEY", b"1") == -1
+    for v in (b"off", b"all", b"csr"):                      # what spmv_generic.cu serves; "csr" is the default
+        assert lib.b200spmv_set_option(b"B200SPMV_GENERIC", v) == 0
+    assert lib.b200spmv_set_option(b"B200SPMV_GENERIC", b"everything") == -1
     n, f, a = ctypes.c_uint64(7), ctypes.c_uint64(7), ctypes.c_uint64(7)
     lib.b200spmv_reset_stats()
     lib.b200spmv_get_stats(ctypes.byref(n), ctypes.byref(f), ctypes.byref(a))

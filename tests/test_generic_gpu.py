@@ -1,9 +1,11 @@
-"""GPU parity of spmv_generic.cu -- the long tail of cusparseSpMV's real-valued argument space: 64-bit
-indices, fp32 A with fp64 x / y / arithmetic, transposes of those and of Sliced-ELL, CSR calls without a workspace.
+"""GPU parity of spmv_generic.cu, CSR part -- the long tail of cusparseSpMV's real-valued argument space:
+64-bit indices (64/64 and 64/32), fp32 A with fp64 x / y / arithmetic, transposes of those, CSR calls without a workspace.
 Every case goes through the C ABI (the cusparse* symbols of libb200spmv.so), is checked against the CPU oracle / scipy on
 the same inputs and against the closed library on the same device buffers, and must be served by OUR kernels
 (b200spmv_get_stats: forwarded unchanged).  A combination the closed library itself refuses must be refused by the shim
 with the same status (cusparseSpMV_bufferSize keeps the real library's verdict).
+These tests ran green on a B200 in round 2 (call N); the COO / Sliced-ELL kernels of the same file and the strided-batch
+SpMM are in tests/test_zz_unverified_gpu.py.
 
 Tolerances: fp64 arithmetic 1e-12, fp32 arithmetic 1e-5 (relative 2-norm), as in test_parity_gpu.py.
 """
@@ -31,7 +33,7 @@ def cs():
 @pytest.fixture(scope="module")
 def b200(cs):
     api = cs.Api("b200")
-    api.set_option("B200SPMV_GENERIC", "on")
+    api.set_option("B200SPMV_GENERIC", "csr")       # the library default
     return api
 
 
@@ -209,53 +211,3 @@ def test_generic_kernels_read_device_scalars(cs, b200):
         b200.cusparseSetPointerMode(op.handle, cs.CUSPARSE_POINTER_MODE_HOST)
         op.close()
         assert relerr(y.cpu().numpy(), reference(off, col, val, rows, cols, x, y0, 0.5, -3.0, transpose)) < 1e-12
-
-
-# ------------------------------------------------------------------------------------------ COO
-@pytest.mark.parametrize("transpose", [False, True])
-@pytest.mark.parametrize("types", ["f64", "f32", "f32_f64"])
-def test_coo_64bit_indices_any_order(cs, b200, closed, types, transpose):
-    rows, cols, base = 6000, 4100, 1
-    off, col, val = matrix(rows, cols, 10, 601)
-    va = val.astype(TYPES[types][0])
-    row = np.repeat(np.arange(rows, dtype=np.int64), np.diff(off))
-    perm = np.random.default_rng(5).permutation(col.size)           # cuSPARSE's COO SpMV takes any order of the entries
-    arrays = dict(row=dev(row[perm] + base), col=dev(col[perm] + base), val=dev(va[perm]))
-    check(cs, b200, closed, "coo", rows, cols, arrays, (off, col, va), base, transpose, types)
-
-
-# ------------------------------------------------------------------------------------------ Sliced-ELL
-@pytest.mark.parametrize("types", ["f64", "f32", "f32_f64"])
-@pytest.mark.parametrize("off_bits,col_bits,slice_size,transpose", [(64, 64, 32, False), (64, 32, 7, False), (64, 64, 7, True),
-                                                                    (32, 32, 32, True), (32, 32, 7, True)])
-def test_sell_index_widths_and_transposes(cs, b200, closed, off_bits, col_bits, slice_size, transpose, types):
-    if (off_bits, col_bits) == (32, 32) and not transpose and types != "f32_f64":
-        pytest.skip("the specialised Sliced-ELL kernels (test_parity_gpu.py)")
-    rows, cols, base = 5013, 3100, 0                                 # the last slice is partial
-    off, col, val = matrix(rows, cols, 6, 701)
-    va = val.astype(TYPES[types][0])
-    so, sc, sv = O.csr_to_sell(off.astype(np.int32), col.astype(np.int32), va, slice_size)
-    arrays = dict(off=dev(so.astype(NPI[off_bits])), col=dev(sc.astype(NPI[col_bits])), val=dev(sv), slice_size=slice_size,
-                  nnz=int(col.size))
-    check(cs, b200, closed, "sell", rows, cols, arrays, (off, col, va), base, transpose, types)
-
-
-# ------------------------------------------------------------------------------------------ switch
-def test_generic_off_hands_the_long_tail_to_the_closed_library(cs, b200):
-    rows = 4000
-    off, col, val = matrix(rows, rows, 8, 801)
-    arrays = dict(off=dev(off), col=dev(col), val=dev(val))
-    x, y0 = O.uniform(5, rows), O.uniform(6, rows)
-    b200.set_option("B200SPMV_GENERIC", "off")
-    try:
-        before = b200.stats()
-        op = cs.SpMVOperator(b200, "csr", rows, rows, arrays)
-        y = dev(y0).clone()
-        op(dev(x), y, 1.0, 0.0)
-        torch.cuda.synchronize()
-        op.close()
-        after = b200.stats()
-        assert after["forwarded"] == before["forwarded"] + 1 and after["native"] == before["native"]
-    finally:
-        b200.set_option("B200SPMV_GENERIC", "on")
-    assert relerr(y.cpu().numpy(), reference(off, col, val, rows, rows, x, y0, 1.0, 0.0, False)) < 1e-12

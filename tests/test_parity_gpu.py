@@ -421,7 +421,7 @@ def test_non_default_stream_and_graph_capture(cs, b200):
 
 def test_unsupported_combinations_are_forwarded_not_broken(cs, b200, closed):
     """What our kernels do not take, the shim must hand to the closed library unchanged -- and count it.  64-bit indices with
-    the generic kernels switched off (B200SPMV_GENERIC=off; with them on: tests/test_generic_gpu.py) stand for that set
+    the generic kernels switched off (B200SPMV_GENERIC=off; with them on, the default: tests/test_generic_gpu.py) stand for that set
     (complex / 16-bit value types, CSC / BSR / Blocked-ELL)."""
     rows = 5000
     off, col, val, x, y0 = rmat_case(rows, 8, torch.float64, 71)
@@ -430,7 +430,7 @@ def test_unsupported_combinations_are_forwarded_not_broken(cs, b200, closed):
     try:
         got = run(cs, b200, "csr", rows, rows, arrays, dev(x), dev(y0), 1.0, 0.0, expect_forward=True)
     finally:
-        b200.set_option("B200SPMV_GENERIC", "on")
+        b200.set_option("B200SPMV_GENERIC", "csr")      # the library default
     assert relerr(got.cpu().numpy(), O.spmv_csr(off, col, val, x)) < 1e-12
 
 
