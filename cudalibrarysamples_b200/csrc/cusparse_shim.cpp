@@ -268,6 +268,18 @@ extern "C" {
 
 const char* b200spmv_version(void) { return "b200spmv 0.1 (sm_100a)"; }
 
+// Which path would cusparseSpMV take for a call of this shape?  0: handed to the closed library, 1: the specialised kernels,
+// 2: the kernels of spmv_generic.cu.  Pure host logic (no CUDA call, no descriptor): the dispatch table under a CPU test.
+int b200spmv_route(int format, int op, int alg, int off_type, int col_type, int a_vtype, int x_vtype, int y_vtype, int compute_type,
+                   int64_t rows, int64_t cols, int64_t nnz) {
+    MatInfo m;
+    m.format = (cusparseFormat_t)format; m.rows = rows; m.cols = cols; m.nnz = nnz;
+    m.off_type = (cusparseIndexType_t)off_type; m.col_type = (cusparseIndexType_t)col_type; m.vtype = (cudaDataType)a_vtype;
+    VecInfo x, y;
+    x.vtype = (cudaDataType)x_vtype; y.vtype = (cudaDataType)y_vtype;
+    return (int)classify((cusparseOperation_t)op, m, x, y, (cudaDataType)compute_type, (cusparseSpMVAlg_t)alg);
+}
+
 // ---------------------------------------------------------------- sparse-matrix descriptors --------------------------
 cusparseStatus_t cusparseCreateCsr(cusparseSpMatDescr_t* d, int64_t rows, int64_t cols, int64_t nnz, void* off, void* col,
                                    void* val, cusparseIndexType_t offT, cusparseIndexType_t colT, cusparseIndexBase_t base,

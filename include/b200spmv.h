@@ -198,6 +198,10 @@ B200SPMV_EXPORT int  b200spmv_set_option(const char* key, const char* value);
  * forwarded == 0 on the hot path. */
 B200SPMV_EXPORT void b200spmv_get_stats(uint64_t* native_calls, uint64_t* forwarded_calls, uint64_t* analyze_calls);
 B200SPMV_EXPORT void b200spmv_reset_stats(void);
+/* Which path cusparseSpMV takes for a call of this shape (enum values of cusparse.h / library_types.h passed as int):
+ * 0 = handed to the closed library, 1 = the specialised 32-bit-index single-type kernels, 2 = spmv_generic.cu.  Host logic only. */
+B200SPMV_EXPORT int b200spmv_route(int format, int op, int alg, int off_type, int col_type, int a_vtype, int x_vtype, int y_vtype,
+                                   int compute_type, int64_t rows, int64_t cols, int64_t nnz);
 /* name of the main kernel the most recent CSR SpMV launched, e.g. "b200::csr_seg_kernel<double>" (bench.py's roofline.kernel) */
 B200SPMV_EXPORT const char* b200spmv_last_csr_kernel(void);
 
