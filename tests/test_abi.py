@@ -92,8 +92,8 @@ def kernel_sass(built_lib, pattern):
     return m.group(0)
 
 
-def test_sass_of_the_default_fp64_csr_kernel(built_lib):
-    """What the default kernel for >= 12 nnz/row (csr_seg_kernel<double>) really emits: 64-bit L1-no-allocate streaming
+def test_sass_of_the_seg_kernel(built_lib):
+    """What the selectable csr_seg_kernel<double> (register accumulation + segmented scan per tile) really emits: 64-bit L1-no-allocate streaming
     loads of val[] (lane-consecutive: 256 B per warp instruction -- per-lane 128-bit loads were measured slower, see
     DESIGN.md), 32-bit ones of col_ind[], x through the read-only path, shuffle / vote / redux based row reduction, no
     tensor cores.  profiles/sass_summary_r2.md holds the per-kernel instruction counts."""
@@ -104,6 +104,29 @@ def test_sass_of_the_default_fp64_csr_kernel(built_lib):
     assert "SHFL" in body and "VOTE" in body and "REDUX" in body
     assert not re.search(r"LDG\.E\S*\.128", body)      # no 128-bit per-lane loads in this kernel
     assert "HMMA" not in body and "UTC" not in body and "UTMA" not in body   # no tensor cores, no tensor-map TMA
+
+
+def test_sass_of_the_headline_kernel(built_lib):
+    """csr_flat_kernel<double> -- what bench.py's headline number runs on (profiles/sass_summary_r2.md has the full table):
+    the val[] / col_ind[] streams as 64- / 32-bit L1-no-allocate loads (lane-consecutive: 256 B / 128 B per warp instruction),
+    x gathered through the read-only path, butterfly + segmented-scan shuffles, no per-lane 128-bit global loads, a CTA
+    barrier only at the stitch, no bulk copies, no tensor cores."""
+    body = kernel_sass(built_lib, "csr_flat_kernelId")
+    assert len(re.findall(r"LDG\.E\.NA\.64", body)) == 8 and len(re.findall(r"LDG\.E\.NA\.CONSTANT", body)) == 8   # 8 steps of 32 per warp chunk
+    assert re.search(r"LDG\.E\.64\.CONSTANT", body)
+    assert "SHFL.BFLY" in body and "SHFL.UP" in body and "VOTE" in body
+    assert not re.search(r"LDG\.E\S*\.128", body)
+    assert len(re.findall(r"\bBAR\.", body)) <= 3
+    assert "UBLKCP" not in body and "HMMA" not in body and "UTC" not in body and "UTMA" not in body
+
+
+def test_sass_summary_in_profiles_is_current(built_lib):
+    """profiles/sass_summary_r2.md is generated from the built library (scripts/sass_summary.py): the committed table must list
+    every kernel the library contains."""
+    table = open(os.path.join(ROOT, "profiles", "sass_summary_r2.md")).read()
+    sass = subprocess.check_output(["cuobjdump", "-sass", built_lib], text=True)
+    kernels = set(re.findall(r"Function : _ZN\d+b200(?:cg|peer)?\d+([a-z0-9_]+_kernel)", sass))     # _ZN4b20015csr_flat_kernelIdE... -> csr_flat_kernel
+    assert kernels and not [k for k in kernels if k not in table]
 
 
 def test_sass_of_the_tma_fed_variant(built_lib):
