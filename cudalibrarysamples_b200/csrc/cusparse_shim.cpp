@@ -697,11 +697,13 @@ static bool get_dnmat(cusparseConstDnMatDescr_t d, DnMatInfo* m) {
 // strided with N entries or shared by the whole batch (A with both strides 0: the sample's "matA broadcast" variant; B with
 // batch count 1).  Returns N (1 = no batch), or 0 for a combination we leave to the real library.
 static int spmm_batch_count(cusparseConstSpMatDescr_t matA, const MatInfo& a, const DnMatInfo& b, const DnMatInfo& c) {
+    const int ab = a.batch < 1 ? 1 : a.batch;
+    if (ab == 1 && b.batch == 1 && c.batch == 1) return 1;    // the ordinary call: nothing to ask the library
+    if (b200::config().generic < 2) return 0;                 // batches: opt-in until run on hardware (config.h)
     int real_a = 1;
     if (real().cusparseSpMatGetStridedBatch(matA, &real_a) != CUSPARSE_STATUS_SUCCESS || real_a < 1) real_a = 1;
-    if (real_a != (a.batch < 1 ? 1 : a.batch)) return 0;      // the batch was set behind our back: we do not know its strides
+    if (real_a != ab) return 0;                               // the batch was set behind our back: we do not know its strides
     const int n = c.batch;
-    if ((real_a > 1 || b.batch > 1 || n > 1) && b200::config().generic < 2) return 0;   // batches: opt-in until run on hardware (config.h)
     if (real_a != 1 && real_a != n) return 0;
     if (b.batch != 1 && b.batch != n) return 0;
     if (n > 1 && c.stride < c.rows * c.cols) return 0;        // overlapping outputs
@@ -779,6 +781,17 @@ cusparseStatus_t cusparseSpMM(cusparseHandle_t handle, cusparseOperation_t opA, 
                              c.order == CUSPARSE_ORDER_ROW, externalBuffer);
     b200::stats().native_calls++;
     return to_status(rc);
+}
+
+// How many products would cusparseSpMM run on our kernel for these descriptors?  0: the call goes to the closed library (a batch
+// layout we do not take, or batches while they are opt-in), 1: an ordinary product, N: a strided batch.  Host logic only (the
+// real library's descriptor calls need no device): under a CPU test.
+int b200spmm_batch_count(const void* matA, const void* matB, const void* matC) {
+    MatInfo a; DnMatInfo b, c;
+    if (!matA || !matB || !matC || !find_mat((cusparseConstSpMatDescr_t)matA, &a) || !get_dnmat((cusparseConstDnMatDescr_t)matB, &b) ||
+        !get_dnmat((cusparseConstDnMatDescr_t)matC, &c))
+        return 0;
+    return spmm_batch_count((cusparseConstSpMatDescr_t)matA, a, b, c);
 }
 
 }  // extern "C"
