@@ -67,6 +67,34 @@ SCRIPT = textwrap.dedent("""
     # a descriptor the shim never saw: found through the real getters, ordinary product only
     A3 = csr(real)
     assert count(A3, dn(1, 0), dn(1, 0)) == 1
+    # every descriptor kind the samples create goes through the shim and stays a REAL descriptor: the real getters see what
+    # the shim was given (spmv_coo_example.c:86-89, spmv_sell_example.c:103-107, spmv_csr_example.c:93-95), set-pointer calls reach both sides
+    fmt = C.c_int(-1)
+    coo = C.c_void_p()
+    assert shim.cusparseCreateCoo(C.byref(coo), C.c_int64(4), C.c_int64(4), C.c_int64(9), col, col, val, I32, 0, F32) == 0
+    assert real.cusparseSpMatGetFormat(coo, C.byref(fmt)) == 0 and fmt.value == 3
+    sell = C.c_void_p()
+    assert shim.cusparseCreateSlicedEll(C.byref(sell), C.c_int64(4), C.c_int64(4), C.c_int64(9), C.c_int64(12), C.c_int64(2), off, col, val,
+                                        I32, I32, 0, F32) == 0
+    assert real.cusparseSpMatGetFormat(sell, C.byref(fmt)) == 0 and fmt.value == 7
+    vec = C.c_void_p()
+    assert shim.cusparseCreateDnVec(C.byref(vec), C.c_int64(4), B, F32) == 0
+    size, vals, vt = C.c_int64(), C.c_void_p(), C.c_int()
+    assert real.cusparseDnVecGet(vec, C.byref(size), C.byref(vals), C.byref(vt)) == 0 and size.value == 4 and vals.value == C.addressof(B)
+    assert shim.cusparseDnVecSetValues(vec, Cm) == 0
+    assert real.cusparseDnVecGetValues(vec, C.byref(vals)) == 0 and vals.value == C.addressof(Cm)
+    off2 = (C.c_int * 5)(0, 1, 2, 3, 4)
+    assert shim.cusparseCsrSetPointers(A1, off2, col, val) == 0
+    r, c_, z, po, pc, pv = C.c_int64(), C.c_int64(), C.c_int64(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    ot, ct, ib, vt2 = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    assert real.cusparseCsrGet(A1, C.byref(r), C.byref(c_), C.byref(z), C.byref(po), C.byref(pc), C.byref(pv), C.byref(ot), C.byref(ct),
+                               C.byref(ib), C.byref(vt2)) == 0 and po.value == C.addressof(off2) and (r.value, c_.value, z.value) == (4, 4, 9)
+    assert shim.cusparseDestroyDnVec(vec) == 0
+    for d in (coo, sell):
+        assert shim.cusparseDestroySpMat(d) == 0
+    # what cusparseSpMV would do with descriptors like these (b200spmv_route), under the default switch
+    mode(b"csr")
+    assert shim.b200spmv_route(1, 0, 0, I32, I32, F32, F32, F32, F32, C.c_int64(4), C.c_int64(4), C.c_int64(9)) == 1
     for d in (A, A1, A2):
         assert shim.cusparseDestroySpMat(d) == 0
     assert real.cusparseDestroySpMat(A3) == 0
