@@ -73,7 +73,7 @@ def kernel_source_sha(kernel="b200::csr_flat_kernel<double>"):
     short = kernel.split("::")[-1].split("<")[0]
     owner = None
     for name in sorted(os.listdir(d)):
-        if name.endswith(".cu") and ("__global__" in open(os.path.join(d, name)).read()) and (" " + short + "(") in open(os.path.join(d, name)).read():
+        if name.endswith((".cu", ".cuh")) and ("__global__" in open(os.path.join(d, name)).read()) and (" " + short + "(") in open(os.path.join(d, name)).read():
             owner = name
             break
     h = hashlib.sha256()

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libb200spmv.so")
 GEN_LIB_PATH = os.path.join(PKG_DIR, "libb200gen.so")
 SOURCES = ["spmv_csr.cu", "spmv_csr_flat.cu", "spmv_csr_short.cu", "spmv_csr_transpose.cu", "spmv_coo_sell.cu", "spmv_generic.cu", "spmm_csr.cu", "cg_fused.cu", "peer_sync.cu", "config.cpp", "cusparse_shim.cpp"]
 GEN_SOURCES = ["workload_gen.cu"]
-HEADERS = ["spmv_common.cuh", "config.h", os.path.join("..", "..", "include", "b200spmv.h"),
+HEADERS = ["spmv_common.cuh", "spmv_generic_kernels.cuh", "config.h", os.path.join("..", "..", "include", "b200spmv.h"),
            os.path.join("..", "..", "include", "b200gen.h")]
 
 NVCC_FLAGS = [

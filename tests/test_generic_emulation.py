@@ -4,9 +4,15 @@ The emulation follows the kernel statement by statement -- the warp-uniform oute
 striding through their row, the shuffle tree with `width = L` (a lane whose partner would fall outside its L-lane segment
 gets its own value back, as __shfl_down_sync does), lane 0 of a segment writing y -- so it pins the index arithmetic and
 the reduction pattern: every row written exactly once, with the complete row sum, for every lane count and for grids
-smaller than the matrix (several trips of the loop).  The GPU parity proper is tests/test_generic_gpu.py."""
+smaller than the matrix (several trips of the loop).  The second half of the file goes further: it compiles the kernels' OWN SOURCE for
+the host and runs it (see there).  The GPU parity proper is tests/test_generic_gpu.py."""
+import ctypes as C
+import os
+import subprocess
+
 import numpy as np
 import pytest
+import scipy.sparse as sp
 
 from oracle import oracle as O
 
@@ -105,3 +111,102 @@ def test_sell_generic_index_arithmetic(S):
     want = O.spmv_csr(off, col, val, x, y0, 1.0, 2.0)
     assert np.linalg.norm(y - want) <= 1e-13 * np.linalg.norm(want)
     assert np.linalg.norm(O.spmv_sell(rows, S, so, sc, sv, x, y0, 1.0, 2.0) - want) <= 1e-13 * np.linalg.norm(want)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The kernels' OWN SOURCE on the CPU: csrc/spmv_generic_kernels.cuh compiled for the host on top of
+# tests/host_emulation/cuda_emulation.h (a real thread per lane, a barrier-based __shfl_down_sync, a locked atomicAdd) and run
+# with the device's launch geometry against scipy / the oracle.  Covers the kernels whose first hardware run is still pending
+# (COO, Sliced-ELL, their transposes) as well as the CSR ones already validated on a B200.
+# ------------------------------------------------------------------------------------------------------------------
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "host_emulation")
+NPI = {0: np.int32, 1: np.int64}
+NPF = {0: np.float32, 1: np.float64}
+CTF = {0: C.c_float, 1: C.c_double}
+# (offsets 64-bit, columns 64-bit, A fp64, x / y fp64): the nine instantiations of spmv_generic.cu's dispatch
+COMBOS = [(0, 0, 0, 0), (0, 0, 0, 1), (0, 0, 1, 1), (1, 0, 0, 0), (1, 0, 0, 1), (1, 0, 1, 1), (1, 1, 0, 0), (1, 1, 0, 1), (1, 1, 1, 1)]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(EMU_DIR, "_build", "libgeneric_emu.so")
+    srcs = [os.path.join(EMU_DIR, "emulate_generic.cpp"), os.path.join(EMU_DIR, "cuda_emulation.h"),
+            os.path.join(ROOT, "cudalibrarysamples_b200", "csrc", "spmv_generic_kernels.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-shared", "-fPIC", "-I" + EMU_DIR,
+                               "-I" + os.path.join(ROOT, "cudalibrarysamples_b200", "csrc"), srcs[0], "-o", out])
+    return C.CDLL(out)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _case(rows, cols, avg, seed, a_dt, xy_dt, transpose, base):
+    off, col, val = O.rmat_csr(rows, avg_nnz=avg, seed=seed, val_seed=seed + 1)
+    col = col % cols
+    val = val.astype(NPF[a_dt])
+    nx, ny = (rows, cols) if transpose else (cols, rows)
+    x, y0 = O.uniform(seed + 2, nx).astype(NPF[xy_dt]), O.uniform(seed + 3, ny).astype(NPF[xy_dt])
+    A = sp.csr_matrix((val.astype(np.float64), col, off), shape=(rows, cols))
+    return off, col, val, x, y0, (A.T if transpose else A)
+
+
+def _tol(xy_dt):
+    return 1e-12 if xy_dt else 2e-5
+
+
+@pytest.mark.parametrize("off64,col64,a_dt,xy_dt", COMBOS)
+@pytest.mark.parametrize("transpose", [0, 1])
+def test_csr_generic_source_on_the_host(emu, off64, col64, a_dt, xy_dt, transpose):
+    rows, cols, base = 300, 211, 1
+    off, col, val, x, y0, M = _case(rows, cols, 7, 40 + off64 + 2 * col64, a_dt, xy_dt, transpose, base)
+    ct = CTF[xy_dt]
+    for lanes_log2, (alpha, beta) in zip((2, 3, 4, 5), ((-1.5, 0.5), (1.0, 0.0), (2.0, 1.0), (0.75, -2.0))):
+        y = y0.copy() if beta != 0 else np.full_like(y0, np.nan)          # beta = 0 never reads y
+        o, c = (off + base).astype(NPI[off64]), (col + base).astype(NPI[col64])
+        rc = emu.emu_csr_generic(off64, col64, a_dt, xy_dt, transpose, lanes_log2, 1, C.c_longlong(rows), C.c_longlong(cols),
+                                 C.c_longlong(col.size), _p(o), _p(c), _p(val), C.c_longlong(base), C.byref(ct(alpha)), C.byref(ct(beta)),
+                                 _p(x), _p(y))
+        assert rc == 0
+        want = alpha * (M @ x.astype(np.float64)) + (beta * y0.astype(np.float64) if beta != 0 else 0.0)
+        assert np.linalg.norm(y - want) <= _tol(xy_dt) * np.linalg.norm(want), (lanes_log2, alpha, beta)
+
+
+@pytest.mark.parametrize("idx64,a_dt,xy_dt", [(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 0, 0), (1, 0, 1), (1, 1, 1)])
+@pytest.mark.parametrize("transpose", [0, 1])
+def test_coo_generic_source_on_the_host(emu, idx64, a_dt, xy_dt, transpose):
+    """Entries in random order; A^T is the same kernel with the index arrays and the shape swapped (the shim's generic_mv)."""
+    rows, cols, base = 300, 211, 1
+    off, col, val, x, y0, M = _case(rows, cols, 7, 60 + idx64, a_dt, xy_dt, transpose, base)
+    row = np.repeat(np.arange(rows), np.diff(off))
+    perm = np.random.default_rng(1).permutation(col.size)
+    r, c, v = (row[perm] + base).astype(NPI[idx64]), (col[perm] + base).astype(NPI[idx64]), val[perm]
+    ct = CTF[xy_dt]
+    for alpha, beta in ((-1.5, 0.5), (1.0, 0.0), (2.0, 1.0)):
+        y = y0.copy() if beta != 0 else np.full_like(y0, np.nan)
+        args = (rows, cols, r, c) if not transpose else (cols, rows, c, r)
+        rc = emu.emu_coo_generic(idx64, a_dt, xy_dt, 1, C.c_longlong(args[0]), C.c_longlong(args[1]), C.c_longlong(col.size), _p(args[2]),
+                                 _p(args[3]), _p(v), C.c_longlong(base), C.byref(ct(alpha)), C.byref(ct(beta)), _p(x), _p(y))
+        assert rc == 0
+        want = alpha * (M @ x.astype(np.float64)) + (beta * y0.astype(np.float64) if beta != 0 else 0.0)
+        assert np.linalg.norm(y - want) <= _tol(xy_dt) * np.linalg.norm(want), (alpha, beta)
+
+
+@pytest.mark.parametrize("off64,col64,a_dt,xy_dt", COMBOS)
+@pytest.mark.parametrize("transpose,S", [(0, 32), (0, 7), (1, 32), (1, 2)])
+def test_sell_generic_source_on_the_host(emu, off64, col64, a_dt, xy_dt, transpose, S):
+    rows, cols, base = 203, 150, 1                                       # partial last slice; base 1: padding column is 0
+    off, col, val, x, y0, M = _case(rows, cols, 5, 80 + S, a_dt, xy_dt, transpose, base)
+    so, sc, sv = O.csr_to_sell((off + base).astype(np.int32), (col + base).astype(np.int32), val, S, base=base)
+    ct = CTF[xy_dt]
+    for alpha, beta in ((-1.5, 0.5), (1.0, 0.0)):
+        y = y0.copy() if beta != 0 else np.full_like(y0, np.nan)
+        o, c = so.astype(NPI[off64]), sc.astype(NPI[col64])
+        rc = emu.emu_sell_generic(off64, col64, a_dt, xy_dt, transpose, 1, C.c_longlong(rows), C.c_longlong(cols), C.c_longlong(S),
+                                  _p(o), _p(c), _p(sv), C.c_longlong(base), C.byref(ct(alpha)), C.byref(ct(beta)), _p(x), _p(y))
+        assert rc == 0
+        want = alpha * (M @ x.astype(np.float64)) + (beta * y0.astype(np.float64) if beta != 0 else 0.0)
+        assert np.linalg.norm(y - want) <= _tol(xy_dt) * np.linalg.norm(want), (alpha, beta)
