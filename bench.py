@@ -716,8 +716,12 @@ def run_ours(args):
         # correctness of the measured result against the oracle, at full size
         rel = float(np.linalg.norm(y.cpu().numpy() - ref) / np.linalg.norm(ref))
         assert rel < 1e-12, f"GPU result differs from the CPU oracle: {rel}"
+        # SURVEY.md 8(d) also asks for the loop "single-threaded exactly as written" (spmv_csr_op_example.c:307-318): 5 repetitions, median
+        med1, times1, _ = cpu_times(h_off, h_col, h_val, h_x, 1, 5)
         cpu = {"value": round(gbs, 3), "unit": UNIT, "cores": threads, "kind": "port", "statistic": "median",
                "sample": f"the full {rows}-row matrix, 21 repetitions, median ({med * 1e3:.2f} ms; min {min(times) * 1e3:.2f}); OpenMP dynamic row chunks",
+               "single_thread": {"value": round(csr_bytes(rows, rows, nnz) / med1 / 1e9, 3), "unit": UNIT, "cores": 1,
+                                 "ms_per_step": round(med1 * 1e3, 2), "sample": "the same matrix, the row loop as the sample writes it, 5 repetitions, median"},
                "gpu_vs_oracle_rel_err": rel}
 
     # ---- extra legs: north-star size, CG ----
