@@ -112,12 +112,13 @@ def check(cs, b200, closed, fmt, rows, cols, arrays, host, base, transpose, type
 
 
 # ------------------------------------------------------------------------------------------ CSR
+# (32-bit indices with one value type run on the specialised kernels: tests/test_parity_gpu.py)
+CSR_CASES = [(o, c, t) for (o, c) in ((64, 64), (64, 32)) for t in ("f64", "f32", "f32_f64")] + [(32, 32, "f32_f64")]
+
+
 @pytest.mark.parametrize("transpose", [False, True])
-@pytest.mark.parametrize("types", ["f64", "f32", "f32_f64"])
-@pytest.mark.parametrize("off_bits,col_bits", [(64, 64), (64, 32), (32, 32)])
+@pytest.mark.parametrize("off_bits,col_bits,types", CSR_CASES)
 def test_csr_index_widths_and_mixed_precision(cs, b200, closed, off_bits, col_bits, types, transpose):
-    if (off_bits, col_bits) == (32, 32) and types != "f32_f64":
-        pytest.skip("32-bit indices with one value type: the specialised kernels (test_parity_gpu.py)")
     rows, cols, base = 6000, 4100, 1
     off, col, val = matrix(rows, cols, 12, 201)
     va = val.astype(TYPES[types][0])

@@ -199,8 +199,6 @@ def test_batched_vs_oracle_and_cusparse(cs, b200, closed, dtype, order):
 @pytest.mark.parametrize("off_bits,col_bits,slice_size,transpose", [(64, 64, 32, False), (64, 32, 7, False), (64, 64, 7, True),
                                                                     (32, 32, 32, True), (32, 32, 7, True)])
 def test_sell_index_widths_and_transposes(cs, b200, closed, off_bits, col_bits, slice_size, transpose, types):
-    if (off_bits, col_bits) == (32, 32) and not transpose and types != "f32_f64":
-        pytest.skip("the specialised Sliced-ELL kernels (test_parity_gpu.py)")
     rows, cols, base = 5013, 3100, 0                                 # the last slice is partial
     off, col, val = matrix(rows, cols, 6, 701)
     va = val.astype(TYPES[types][0])
