@@ -210,3 +210,59 @@ def test_sell_generic_source_on_the_host(emu, off64, col64, a_dt, xy_dt, transpo
         assert rc == 0
         want = alpha * (M @ x.astype(np.float64)) + (beta * y0.astype(np.float64) if beta != 0 else 0.0)
         assert np.linalg.norm(y - want) <= _tol(xy_dt) * np.linalg.norm(want), (alpha, beta)
+
+
+def _lens_matrix(lens, cols, seed):
+    rng = np.random.default_rng(seed)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    col = rng.integers(0, max(cols, 1), int(off[-1])).astype(np.int64)
+    val = rng.uniform(-1, 1, int(off[-1]))
+    return off, col, val
+
+
+EDGE_SHAPES = {
+    "one_by_one_empty": ([0], 1),
+    "one_by_one": ([1], 1),
+    "single_row": ([37], 50),
+    "single_column": ([1] * 40, 1),
+    "all_rows_empty": ([0] * 33, 7),
+    "first_and_last_rows_empty": ([0, 0, 5, 1, 0, 9, 0], 12),
+    "33_rows_one_long": ([1] * 32 + [300], 64),
+    "duplicate_columns": ([4, 4, 4], 2),
+}
+
+
+@pytest.mark.parametrize("name", list(EDGE_SHAPES))
+def test_generic_sources_on_degenerate_shapes(emu, name):
+    """CSR (every lane count), COO and Sliced-ELL (slice sizes below, at and above the row count), A and A^T, on the shapes where
+    index arithmetic goes wrong first; fp64 with 64-bit indices, base 0; grid of one CTA."""
+    lens, cols = EDGE_SHAPES[name]
+    rows = len(lens)
+    off, col, val = _lens_matrix(np.array(lens), cols, 7)
+    A = sp.csr_matrix((val, col, off), shape=(rows, cols))
+    row = np.repeat(np.arange(rows, dtype=np.int64), np.diff(off))
+    one, half = C.c_double(1.25), C.c_double(-0.5)
+    LL = C.c_longlong
+    for transpose in (0, 1):
+        M = A.T if transpose else A
+        nx, ny = (rows, cols) if transpose else (cols, rows)
+        x, y0 = O.uniform(1, nx), O.uniform(2, ny)
+        want = 1.25 * (M @ x) - 0.5 * y0
+        tol = 1e-13 * max(np.linalg.norm(want), 1.0)
+        for lanes_log2 in (2, 3, 4, 5):
+            y = y0.copy()
+            assert emu.emu_csr_generic(1, 1, 1, 1, transpose, lanes_log2, 1, LL(rows), LL(cols), LL(col.size), _p(off), _p(col), _p(val), LL(0),
+                                       C.byref(one), C.byref(half), _p(x), _p(y)) == 0
+            assert np.linalg.norm(y - want) <= tol, ("csr", transpose, lanes_log2)
+        y = y0.copy()
+        a = (rows, cols, row, col) if not transpose else (cols, rows, col, row)
+        assert emu.emu_coo_generic(1, 1, 1, 1, LL(a[0]), LL(a[1]), LL(col.size), _p(a[2]), _p(a[3]), _p(val), LL(0), C.byref(one), C.byref(half),
+                                   _p(x), _p(y)) == 0
+        assert np.linalg.norm(y - want) <= tol, ("coo", transpose)
+        for S in (1, 2, 32, 64):
+            so, sc, sv = O.csr_to_sell(off.astype(np.int32), col.astype(np.int32), val, S)
+            so, sc = so.astype(np.int64), sc.astype(np.int64)
+            y = y0.copy()
+            assert emu.emu_sell_generic(1, 1, 1, 1, transpose, 1, LL(rows), LL(cols), LL(S), _p(so), _p(sc), _p(sv), LL(0), C.byref(one),
+                                        C.byref(half), _p(x), _p(y)) == 0
+            assert np.linalg.norm(y - want) <= tol, ("sell", transpose, S)
