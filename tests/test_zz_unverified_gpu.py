@@ -10,7 +10,8 @@ CLOSED library an unsorted COO list (a bug of that version of this file: cuSPARS
 CUDA context did not survive that call and nothing below got a meaningful run.  Until they have one, every test here is
 marked xfail(strict=False): the driver's `pytest -m gpu` reports them as XPASS (kernel correct: flip the default) or XFAIL
 without turning the validated suite red, the file sorts last so that a fault here cannot disturb another test, and inside the
-file the order is least risky first.  The checks themselves are the usual ones: CPU oracle / scipy on the same inputs, the
+file the order is least risky first (the Sliced-ELL cases, where it is not known which index widths and transposes the
+closed library itself accepts, come last).  The checks themselves are the usual ones: CPU oracle / scipy on the same inputs, the
 closed library on the same device buffers (only with input it accepts), served by OUR kernels (forwarded unchanged).
 
 Tolerances: fp64 arithmetic 1e-12, fp32 arithmetic 1e-5 (relative 2-norm), as in test_parity_gpu.py.
@@ -194,20 +195,6 @@ def test_batched_vs_oracle_and_cusparse(cs, b200, closed, dtype, order):
     assert relerr(got, lib) < tol
 
 
-# ------------------------------------------------------------------------------------------ Sliced-ELL
-@pytest.mark.parametrize("types", ["f64", "f32", "f32_f64"])
-@pytest.mark.parametrize("off_bits,col_bits,slice_size,transpose", [(64, 64, 32, False), (64, 32, 7, False), (64, 64, 7, True),
-                                                                    (32, 32, 32, True), (32, 32, 7, True)])
-def test_sell_index_widths_and_transposes(cs, b200, closed, off_bits, col_bits, slice_size, transpose, types):
-    rows, cols, base = 5013, 3100, 0                                 # the last slice is partial
-    off, col, val = matrix(rows, cols, 6, 701)
-    va = val.astype(TYPES[types][0])
-    so, sc, sv = O.csr_to_sell(off.astype(np.int32), col.astype(np.int32), va, slice_size)
-    arrays = dict(off=dev(so.astype(NPI[off_bits])), col=dev(sc.astype(NPI[col_bits])), val=dev(sv), slice_size=slice_size,
-                  nnz=int(col.size))
-    check(cs, b200, closed, "sell", rows, cols, arrays, (off, col, va), base, transpose, types)
-
-
 # ------------------------------------------------------------------------------------------ COO
 @pytest.mark.parametrize("transpose", [False, True])
 @pytest.mark.parametrize("types", ["f64", "f32", "f32_f64"])
@@ -233,3 +220,17 @@ def test_coo_64bit_indices_any_order(cs, b200, transpose):
     x, y0 = O.uniform(7, nx), O.uniform(8, ny)
     got = spmv(cs, b200, "coo", rows, cols, arrays, dev(x), dev(y0).clone(), -1.5, 0.5, base, transpose, torch.float64).cpu().numpy()
     assert relerr(got, reference(off, col, val, rows, cols, x, y0, -1.5, 0.5, transpose)) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------ Sliced-ELL
+@pytest.mark.parametrize("types", ["f64", "f32", "f32_f64"])
+@pytest.mark.parametrize("off_bits,col_bits,slice_size,transpose", [(64, 64, 32, False), (64, 32, 7, False), (64, 64, 7, True),
+                                                                    (32, 32, 32, True), (32, 32, 7, True)])
+def test_sell_index_widths_and_transposes(cs, b200, closed, off_bits, col_bits, slice_size, transpose, types):
+    rows, cols, base = 5013, 3100, 0                                 # the last slice is partial
+    off, col, val = matrix(rows, cols, 6, 701)
+    va = val.astype(TYPES[types][0])
+    so, sc, sv = O.csr_to_sell(off.astype(np.int32), col.astype(np.int32), va, slice_size)
+    arrays = dict(off=dev(so.astype(NPI[off_bits])), col=dev(sc.astype(NPI[col_bits])), val=dev(sv), slice_size=slice_size,
+                  nnz=int(col.size))
+    check(cs, b200, closed, "sell", rows, cols, arrays, (off, col, va), base, transpose, types)
