@@ -762,6 +762,8 @@ def run_ours(args):
     if rank == 0:
         launches = {"b200::csr_flat_kernel<double>": 2, "b200::csr_seg_kernel<double>": 2, "b200::csr_tile_kernel<double>": 2,
                     "b200::csr_rowwise_kernel<double>": 2}.get(kname, 1) * (getattr(args, "_npanels", 1) if dist_on else 1)
+        if dist_on and isinstance(exchange, str) and exchange.startswith("x shards in symmetric memory"):
+            launches += 1          # the device-side barrier kernel of the p2p exchange (csrc/peer_sync.cu); the peer copies are copy-engine work
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
