@@ -566,39 +566,62 @@ def run_ours(args):
                 return cs.SpMVOperator(api, "csr", r, c, arrays, preprocess=True)
             finally:
                 api.set_option("B200SPMV_FLAT", "auto")
-        sh = ShardedCsr(off, col, val, rank, world, make_local, exchange=args.exchange, row_weight=args.row_weight)   # R-MAT rows read every x block
+        def set_up(exchange_mode, overlap):
+            """Shards, operators, the step callables, and the parity check of the sharded product at full size: every rank checks
+            its y shard against the closed library run on the same local arrays and the gathered x."""
+            sh = ShardedCsr(off, col, val, rank, world, make_local, exchange=exchange_mode, overlap=overlap, row_weight=args.row_weight)   # R-MAT rows read every x block
+            xs = sh.new_x_shard(x)
+            ys = sh.new_y_shard()
+            step = sh.make_step(xs, ys, in_place=True)      # x is constant over the timed loop: published once, exchanged every step
+            e2e_inner = sh.make_step(xs, ys, graph=False)   # e2e: a new x arrives from the host every step -> staged + exchanged
+            if sh.panels:      # the local product alone = all column panels back to back, no exchange
+                def local_call():
+                    for c in sh.panel_calls:
+                        c()
+            else:
+                local_call = sh.local_op.prebuilt(sh.x_full, ys, 1.0, 0.0)
+            local = dict(rows=sh.rows, nnz=sh.nnz, x_block=sh.x_block)
+            step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            capi = cs.Api("cusparse")
+            cop = cs.SpMVOperator(capi, "csr", sh.rows, sh.cols_padded, dict(off=sh.off, col=sh.col, val=sh.val), preprocess=True)
+            yc = torch.zeros_like(ys)
+            cop(sh.x_full, yc, 1.0, 0.0)
+            torch.cuda.synchronize()
+            shard_rel = (torch.linalg.norm(ys - yc) / torch.linalg.norm(yc)).reshape(1)
+            dist.all_reduce(shard_rel, op=dist.ReduceOp.MAX)
+            local["max_rel_diff_vs_cusparse_over_ranks"] = float(shard_rel.item())
+            assert local["max_rel_diff_vs_cusparse_over_ranks"] < 1e-12
+            cop.close()
+            return sh, xs, ys, step, e2e_inner, local_call, local
+
+        # The column-panel step (N >= 4) has only ever run at N = 2 (forced); if its set-up or its parity check raises -- the same
+        # Python error on every rank, the code path is rank-symmetric -- the run falls back to the plain step that was measured at
+        # N = 2 (exchange, then one local product), then to the NCCL all-gather of round 1, and SAYS SO in the JSON line.
+        attempts = [(args.exchange, True), (args.exchange, False), ("allgather", False)]
+        if world < int(os.environ.get("B200SPMV_PANELS_FROM", "4")):
+            attempts = attempts[1:]                         # no panels at this N anyway
+        fallback_notes = []
+        for k, (mode, overlap) in enumerate(attempts):
+            try:
+                sh, xs, ys, step, e2e_inner, local_call, local = set_up(mode, overlap)
+                break
+            except Exception as e:  # pragma: no cover (GPU boxes only)
+                if k == len(attempts) - 1:
+                    raise
+                fallback_notes.append(f"exchange={mode} overlap={overlap}: {e!r}")
+                print(f"[bench] rank {rank}: {fallback_notes[-1]} -- falling back", file=sys.stderr, flush=True)
+                torch.cuda.synchronize()
+                dist.barrier()
+        if fallback_notes:
+            local["fallback_from"] = fallback_notes
         del off, col, val
         torch.cuda.empty_cache()
-        xs = sh.new_x_shard(x)
-        ys = sh.new_y_shard()
-        step = sh.make_step(xs, ys, in_place=True)      # x is constant over the timed loop: published once, exchanged every step
-        e2e_inner = sh.make_step(xs, ys, graph=False)   # e2e: a new x arrives from the host every step -> staged + exchanged
         args._panels = sh.panels
         args._npanels = len(sh.panel_ops) if sh.panels else 1
-        if sh.panels:      # the local product alone = all column panels back to back, no exchange
-            def local_call():
-                for c in sh.panel_calls:
-                    c()
-        else:
-            local_call = sh.local_op.prebuilt(sh.x_full, ys, 1.0, 0.0)
         exchange = sh.describe_exchange()
         kernel_bytes = csr_bytes(sh.rows, sh.cols_padded, sh.nnz)
-        local = dict(rows=sh.rows, nnz=sh.nnz, x_block=sh.x_block)
-        # parity of the sharded product at full size: every rank checks its y shard against the closed library run
-        # on the same local arrays and the gathered x (max relative difference over ranks goes into the JSON line)
-        step()
-        torch.cuda.synchronize()
-        dist.barrier()
-        capi = cs.Api("cusparse")
-        cop = cs.SpMVOperator(capi, "csr", sh.rows, sh.cols_padded, dict(off=sh.off, col=sh.col, val=sh.val), preprocess=True)
-        yc = torch.zeros_like(ys)
-        cop(sh.x_full, yc, 1.0, 0.0)
-        torch.cuda.synchronize()
-        shard_rel = (torch.linalg.norm(ys - yc) / torch.linalg.norm(yc)).reshape(1)
-        dist.all_reduce(shard_rel, op=dist.ReduceOp.MAX)
-        local["max_rel_diff_vs_cusparse_over_ranks"] = float(shard_rel.item())
-        assert local["max_rel_diff_vs_cusparse_over_ranks"] < 1e-12
-        cop.close()
 
     for _ in range(max(args.warmup, 3)):
         step()
