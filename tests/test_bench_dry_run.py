@@ -1,4 +1,4 @@
-"""CPU, gloo: bench.run_ours -- the real multi-GPU branch of bench.py -- executed end to end at world 2 and 4 with only the
+"""CPU, gloo: bench.run_ours -- the real multi-GPU branch of bench.py -- executed end to end at world 2, 4 and 8 with only the
 device layer replaced (tests/bench_dry_run_worker.py): column panels, staged set-up, timing loops, exchange-alone diagnostic,
 e2e loop, CG leg, JSON line.  Round 2 lost its N >= 4 runs to a one-line host bug in exactly this code; it fails here now."""
 import json
@@ -37,7 +37,7 @@ def dry_run(world, tmp_path, fail_first=False):
     return json.loads(open(out).read().strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_bench_multi_gpu_branch_runs_end_to_end(world, tmp_path):
     line = dry_run(world, tmp_path)
     assert line["n_gpus"] == world and line["metric"] == "csr_spmv_fp64_effective_hbm_bandwidth" and line["scaling"] == "weak"
