@@ -60,3 +60,18 @@ def test_bench_falls_back_and_says_so(tmp_path):
     assert len(per["fallback_from"]) == 1 and "injected failure" in per["fallback_from"][0]
     assert "panel" not in line["exchange"]                                           # the plain step ran
     assert per["max_rel_diff_vs_cusparse_over_ranks"] < 1e-12 and line["value"] > 0
+
+
+def test_bench_single_gpu_branch_runs_end_to_end(tmp_path):
+    """N = 1: the headline line -- timing loop through the prebuilt C-ABI call, the pipelined e2e loop (its result compared with the
+    device-resident one), cpu_baseline with the GPU result checked against the oracle, the single-thread baseline, the roofline block."""
+    line = dry_run(1, tmp_path)
+    assert line["n_gpus"] == 1 and line["value"] > 0 and line["config"]["rows"] == 1500 and line["exchange"] is None
+    assert line["e2e"]["h2d_bytes_per_step"] == 1500 * 8 and line["e2e"]["d2h_bytes_per_step"] == 1500 * 8 and line["e2e"]["value"] > 0
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] == "port" and cpu["gpu_vs_oracle_rel_err"] < 1e-12 and cpu["value"] > 0
+    assert cpu["single_thread"]["cores"] == 1 and cpu["single_thread"]["value"] > 0
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and r["kernel"] == "b200::csr_flat_kernel<double>" and 0 < r["frac"] and r["algorithmic_bytes_per_launch"] > 0
+    assert r["traffic"] is not None or "traffic_note" in r
+    assert line["gpu_launches"] == 2 * 3 and line["forwarded_calls_in_timed_region"] == 0
